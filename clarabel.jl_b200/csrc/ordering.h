@@ -1,0 +1,20 @@
+// Host-side fill-reducing orderings (see ordering.cpp).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace cb200 {
+void build_sym_graph(int64_t n, const int64_t* Ap, const int64_t* Ai,
+                     std::vector<int64_t>& xadj, std::vector<int32_t>& adj);
+void amd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                     int32_t* perm_out);
+void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                    int32_t leaf_size, int32_t* perm_out);
+}  // namespace cb200
+
+extern "C" {
+int32_t cb200_order_amd(int64_t n, const int64_t* colptr, const int64_t* rowval,
+                        double dense_scale, int64_t* perm);
+int32_t cb200_order_nd(int64_t n, const int64_t* colptr, const int64_t* rowval,
+                       double dense_scale, int64_t leaf_size, int64_t* perm);
+}
