@@ -7,7 +7,7 @@ in csrc/ (hand-written sm_100a CUDA + host C++ symbolic analysis) behind the C-A
 include/clarabel_b200.h; the Python modules here are the host-side mirror of the reference's
 interface (the Julia toolchain is absent from this image) and the caller harness.
 """
-from . import settings, cones, problemdata, kkt_assembly, kktsystem, solver  # noqa: F401
+from . import settings, cones, problemdata, kkt_assembly, kktsystem, solver, problems  # noqa: F401
 from .settings import Settings  # noqa: F401
 from .cones import (ZeroConeT, NonnegativeConeT, SecondOrderConeT, PSDTriangleConeT,  # noqa: F401
                     CompositeCone)

@@ -1,0 +1,8 @@
+#pragma once
+#include <string>
+#include "symbolic.h"
+struct cb200_settings;
+namespace cb200 {
+void set_error(const std::string& s);
+SymbolicOptions options_from_settings(const cb200_settings* st);
+}

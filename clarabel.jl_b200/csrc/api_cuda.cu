@@ -1,0 +1,710 @@
+// C-ABI implementation of the device-resident KKT solver (include/clarabel_b200.h).
+// Host orchestration only: every numeric operation is a kernel from kernels.cuh.  There is no
+// CPU fallback: if CUDA is unavailable every entry point returns a negative status.
+#include "../../include/clarabel_b200.h"
+#include "symbolic.h"
+#include "api_common.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace cb200 {
+
+#define CUDA_OK(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                \
+            return -100 - (int)_e;                                                        \
+        }                                                                                 \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        free(); n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t st = 0) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free(); }
+};
+
+struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0; };
+
+constexpr int NSMALL = 6;
+static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 160};
+constexpr int NSOLVE = 4;
+static const int kSolveNf[NSOLVE] = {32, 256, 1024, 1 << 30};
+
+struct LevelPlan {
+    Batch small[NSMALL];
+    Batch large;
+    Batch solve[NSOLVE];
+    int64_t wtotal = 0;        // doubles of W workspace needed by the large batch
+};
+
+struct Timers {
+    enum { CONE = 0, FACTOR = 1, SOLVE = 2, SPMV = 3, NPH = 4 };
+    double ms[NPH] = {0, 0, 0, 0};
+    double nfactor = 0, nsolve = 0, nlaunch = 0;
+    std::vector<cudaEvent_t> pool;
+    struct Seg { int ph; cudaEvent_t a, b; };
+    std::vector<Seg> open;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void begin(int ph, cudaStream_t st) { Seg s{ph, get(), get()}; cudaEventRecord(s.a, st); open.push_back(s); }
+    void end(cudaStream_t st) { cudaEventRecord(open.back().b, st); }
+    void collect() {      // call after a stream synchronise
+        for (auto& s : open) { float t = 0; cudaEventElapsedTime(&t, s.a, s.b); ms[s.ph] += t; }
+        open.clear(); used = 0;
+    }
+    ~Timers() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
+}  // namespace cb200
+
+using namespace cb200;
+
+struct cb200_handle {
+    cb200_settings st;
+    Symbolic S;
+    int64_t N = 0, nnzK = 0, base = 0;
+    cudaStream_t stream = nullptr;
+    // K (original order, upper CSC) + row-wise index for the symmetric product
+    DevBuf<int64_t> d_cp; DevBuf<int32_t> d_ri; DevBuf<double> d_nz;
+    DevBuf<int64_t> d_tp; DevBuf<int32_t> d_tc; DevBuf<int64_t> d_tpos;
+    DevBuf<int64_t> d_amap, d_diagidx;
+    DevBuf<int8_t> d_dsign_perm, d_dsign_orig;
+    DevBuf<int32_t> d_perm;
+    // symbolic
+    DevBuf<int32_t> d_sn_first, d_rows, d_rel, d_child_ptr, d_child_list, d_batches;
+    DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff;
+    // numeric
+    DevBuf<double> d_L, d_U, d_W, d_D, d_Dinv, d_uvec;
+    DevBuf<double> d_b, d_x, d_e, d_dx, d_y, d_rx, d_rz;
+    DevBuf<double> d_eps; DevBuf<unsigned long long> d_scal;   // [0] max|diag|, [1] normb, [2] norme
+    DevBuf<unsigned int> d_nreg;
+    std::vector<LevelPlan> plan;
+    std::vector<int64_t> h_woff;
+    bool have_diag = false;
+    // fused (outer) boundary state
+    bool maps_set = false;
+    int64_t n = 0, m = 0, p = 0;
+    DevBuf<int64_t> d_mapP, d_mapA;
+    // diagonal Hs entries
+    int64_t ndiag = 0;
+    DevBuf<int8_t> d_dg_kind; DevBuf<int32_t> d_dg_midx, d_dg_cone; DevBuf<int64_t> d_dg_map;
+    // dense SOC
+    int32_t nsocd = 0;
+    DevBuf<int32_t> d_sd_moff, d_sd_dim, d_sd_socid; DevBuf<int64_t> d_sd_hoff;
+    DevBuf<int64_t> d_mapHs;
+    // sparse SOC expansion
+    int64_t nexp = 0; int32_t nsocs = 0;
+    DevBuf<int32_t> d_ex_src, d_ex_cone, d_exD_cone; DevBuf<int64_t> d_mapu, d_mapv, d_mapD;
+    // PSD
+    int32_t npsd = 0, psd_maxn = 0;
+    DevBuf<int32_t> d_psd_side; DevBuf<int64_t> d_psd_roff, d_psd_hoff;
+    DevBuf<double> d_psd_R, d_psd_A;
+    int64_t psd_rtotal = 0;
+    // cone state
+    int64_t nsoc = 0, nsocrows = 0;
+    DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
+    double last_eps = 0;
+    Timers tm;
+};
+
+namespace {
+
+DevSym devsym(cb200_handle* h) {
+    DevSym d;
+    d.sn_first = h->d_sn_first.p; d.rows_ptr = h->d_rows_ptr.p; d.rows = h->d_rows.p; d.rel = h->d_rel.p;
+    d.child_ptr = h->d_child_ptr.p; d.child_list = h->d_child_list.p;
+    d.panel_off = h->d_panel_off.p; d.upd_off = h->d_upd_off.p; d.dsign = h->d_dsign_perm.p;
+    return d;
+}
+
+inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+#define LAUNCH(h) ((h)->tm.nlaunch += 1)
+
+template <int T>
+int launch_small(cb200_handle* h, const Batch& b, int nfcap, RegParams rp) {
+    if (b.cnt == 0) return 0;
+    size_t sm = (size_t)b.maxnf * b.maxnf * sizeof(double);
+    (void)nfcap;
+    k_factor_small<T><<<b.cnt, T, sm, h->stream>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
+                                                   h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
+    LAUNCH(h);
+    return 0;
+}
+
+template <int T> void launch_fwd(cb200_handle* h, const Batch& b) {
+    if (b.cnt == 0) return;
+    k_fwd<T><<<b.cnt, T, (size_t)b.maxnf * sizeof(double), h->stream>>>(
+        devsym(h), h->d_batches.p + b.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
+    LAUNCH(h);
+}
+template <int T> void launch_bwd(cb200_handle* h, const Batch& b) {
+    if (b.cnt == 0) return;
+    k_bwd<T><<<b.cnt, T, (size_t)b.maxnf * sizeof(double), h->stream>>>(
+        devsym(h), h->d_batches.p + b.off, h->d_L.p, h->d_Dinv.p, h->d_y.p);
+    LAUNCH(h);
+}
+
+// zero the update blocks of the large fronts of one level
+__global__ void k_zero_upd(DevSym S, const int32_t* batch, double* Ust) {
+    const int s = batch[blockIdx.y];
+    const int64_t nr = S.rows_ptr[s + 1] - S.rows_ptr[s];
+    double* U = Ust + S.upd_off[s];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nr * nr;
+         i += (int64_t)gridDim.x * blockDim.x) U[i] = 0.0;
+}
+
+// numeric factorisation of whatever is in d_nz (+ optional on-device static regularisation)
+int factor(cb200_handle* h, bool static_reg) {
+    cudaStream_t st = h->stream;
+    const auto& S = h->S;
+    h->tm.begin(Timers::FACTOR, st);
+    CUDA_OK(cudaMemsetAsync(h->d_L.p, 0, h->d_L.n * sizeof(double), st));
+    CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), st));
+    if (h->nnzK) { k_scatter<<<nblk(h->nnzK, 256), 256, 0, st>>>(h->d_nz.p, h->d_amap.p, h->nnzK, h->d_L.p); LAUNCH(h); }
+    if (static_reg && h->st.static_regularization_enable && h->N) {
+        CUDA_OK(cudaMemsetAsync(h->d_scal.p, 0, sizeof(unsigned long long), st));
+        k_diag_absmax<<<std::min(nblk(h->N, 256), 1184), 256, 0, st>>>(h->d_nz.p, h->d_diagidx.p, h->N, h->d_scal.p);
+        k_compute_eps<<<1, 1, 0, st>>>(h->d_scal.p, h->st.static_regularization_constant,
+                                       h->st.static_regularization_proportional, h->d_eps.p);
+        k_shift_diag<<<nblk(h->N, 256), 256, 0, st>>>(h->d_nz.p, h->d_diagidx.p, h->d_amap.p,
+                                                      h->d_dsign_orig.p, h->d_eps.p, h->N, h->d_L.p);
+        h->tm.nlaunch += 3;
+    }
+    RegParams rp{h->st.dynamic_regularization_eps, h->st.dynamic_regularization_delta,
+                 h->st.dynamic_regularization_enable};
+    DevSym ds = devsym(h);
+    for (int lv = 0; lv < S.nlevels; ++lv) {
+        const LevelPlan& P = h->plan[lv];
+        launch_small<32>(h, P.small[0], 16, rp);
+        launch_small<64>(h, P.small[1], 32, rp);
+        launch_small<128>(h, P.small[2], 64, rp);
+        launch_small<256>(h, P.small[3], 96, rp);
+        launch_small<256>(h, P.small[4], 128, rp);
+        launch_small<256>(h, P.small[5], 160, rp);
+        const Batch& B = P.large;
+        if (B.cnt) {
+            const int32_t* bl = h->d_batches.p + B.off;
+            const int64_t* wo = h->d_woff.p + B.off;
+            int maxnr = B.maxnf;   // upper bound
+            k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)maxnr * maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
+            k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
+            h->tm.nlaunch += 2;
+            for (int kb = 0; kb < B.maxns; kb += LNB) {
+                int rows_below = B.maxnf - kb;
+                k_panel_large<<<dim3(std::max(1, nblk(rows_below, LTR)), B.cnt), LTR, 0, st>>>(
+                    ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
+                int T = nblk(rows_below, UT);
+                k_update_large<<<dim3(T * (T + 1) / 2, B.cnt), 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_U.p,
+                                                                             h->d_W.p, wo);
+                h->tm.nlaunch += 2;
+            }
+        }
+    }
+    h->tm.end(st);
+    h->tm.nfactor += 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// y (permuted, in d_y) <- K^-1 : forward, diagonal, backward
+int tri_solve(cb200_handle* h, const double* d_rhs, double* d_sol) {
+    cudaStream_t st = h->stream;
+    const auto& S = h->S;
+    h->tm.begin(Timers::SOLVE, st);
+    if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
+    for (int lv = 0; lv < S.nlevels; ++lv) {
+        const LevelPlan& P = h->plan[lv];
+        launch_fwd<32>(h, P.solve[0]); launch_fwd<64>(h, P.solve[1]);
+        launch_fwd<128>(h, P.solve[2]); launch_fwd<256>(h, P.solve[3]);
+    }
+    for (int lv = S.nlevels - 1; lv >= 0; --lv) {
+        const LevelPlan& P = h->plan[lv];
+        launch_bwd<32>(h, P.solve[0]); launch_bwd<64>(h, P.solve[1]);
+        launch_bwd<128>(h, P.solve[2]); launch_bwd<256>(h, P.solve[3]);
+    }
+    if (h->N) { k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h); }
+    h->tm.end(st);
+    h->tm.nsolve += 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// e = b - K xi ; norm bits accumulated into d_scal[slot]
+int residual(cb200_handle* h, const double* d_xi, double* d_e, int slot) {
+    cudaStream_t st = h->stream;
+    h->tm.begin(Timers::SPMV, st);
+    CUDA_OK(cudaMemsetAsync(h->d_scal.p + slot, 0, sizeof(unsigned long long), st));
+    if (h->N) {
+        k_residual<<<nblk(h->N * 32, 256), 256, 0, st>>>(h->N, h->d_cp.p, h->d_ri.p, h->d_nz.p, h->d_tp.p,
+                                                         h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p, d_e,
+                                                         h->d_scal.p + slot);
+        LAUNCH(h);
+    }
+    h->tm.end(st);
+    return 0;
+}
+
+int read_scalars(cb200_handle* h, double* out, int first, int count) {
+    unsigned long long bits[4];
+    CUDA_OK(cudaMemcpyAsync(bits, h->d_scal.p + first, count * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < count; ++i) { long long b = (long long)bits[i]; std::memcpy(&out[i], &b, 8); }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                     const int64_t* Dsigns, const cb200_settings* stp, cb200_handle** out) {
+    try {
+        cb200_settings st;
+        if (stp) st = *stp; else cb200_default_settings(&st);
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            set_error("cb200_create: no CUDA device available (this backend has no CPU fallback)");
+            return -3;
+        }
+        CUDA_OK(cudaSetDevice(st.device));
+        auto* h = new cb200_handle();
+        h->st = st; h->N = N; h->base = st.index_base;
+        const int64_t base = st.index_base;
+        std::vector<int64_t> cp(N + 1), ri;
+        for (int64_t i = 0; i <= N; ++i) cp[i] = colptr[i] - base;
+        const int64_t nnz = cp[N];
+        h->nnzK = nnz;
+        ri.resize(nnz);
+        for (int64_t i = 0; i < nnz; ++i) ri[i] = rowval[i] - base;
+        symbolic_analyze(N, cp.data(), ri.data(), options_from_settings(&st), nullptr, h->S);
+        const Symbolic& S = h->S;
+        CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaStream_t s = h->stream;
+        // ---- K
+        std::vector<int32_t> ri32(ri.begin(), ri.end());
+        CUDA_OK(h->d_cp.upload(cp, s)); CUDA_OK(h->d_ri.upload(ri32, s));
+        CUDA_OK(h->d_nz.alloc(nnz));
+        if (nnz) CUDA_OK(cudaMemcpyAsync(h->d_nz.p, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+        // row-wise index of the strictly-upper entries + diagonal positions
+        std::vector<int64_t> tp(N + 1, 0), diagidx(N, -1);
+        for (int64_t j = 0; j < N; ++j)
+            for (int64_t p = cp[j]; p < cp[j + 1]; ++p) {
+                if (ri[p] == j) diagidx[j] = p; else if (ri[p] < j) tp[ri[p] + 1]++;
+            }
+        for (int64_t j = 0; j < N; ++j) tp[j + 1] += tp[j];
+        std::vector<int32_t> tc(tp[N]); std::vector<int64_t> tpos(tp[N]);
+        {
+            std::vector<int64_t> pos(tp.begin(), tp.end() - 1);
+            for (int64_t j = 0; j < N; ++j)
+                for (int64_t p = cp[j]; p < cp[j + 1]; ++p)
+                    if (ri[p] < j) { int64_t q = pos[ri[p]]++; tc[q] = (int32_t)j; tpos[q] = p; }
+        }
+        CUDA_OK(h->d_tp.upload(tp, s)); CUDA_OK(h->d_tc.upload(tc, s)); CUDA_OK(h->d_tpos.upload(tpos, s));
+        h->have_diag = std::all_of(diagidx.begin(), diagidx.end(), [](int64_t v) { return v >= 0; });
+        if (h->have_diag) CUDA_OK(h->d_diagidx.upload(diagidx, s));
+        CUDA_OK(h->d_amap.upload(S.a_map, s));
+        std::vector<int8_t> dsp(N), dso(N);
+        for (int64_t k = 0; k < N; ++k) {
+            dso[k] = (int8_t)(Dsigns ? (Dsigns[k] >= 0 ? 1 : -1) : 1);
+        }
+        for (int64_t k = 0; k < N; ++k) dsp[k] = dso[S.perm[k]];
+        CUDA_OK(h->d_dsign_perm.upload(dsp, s)); CUDA_OK(h->d_dsign_orig.upload(dso, s));
+        CUDA_OK(h->d_perm.upload(S.perm, s));
+        // ---- symbolic
+        CUDA_OK(h->d_sn_first.upload(S.sn_first, s)); CUDA_OK(h->d_rows_ptr.upload(S.rows_ptr, s));
+        CUDA_OK(h->d_rows.upload(S.rows, s)); CUDA_OK(h->d_rel.upload(S.rel, s));
+        CUDA_OK(h->d_child_ptr.upload(S.child_ptr, s)); CUDA_OK(h->d_child_list.upload(S.child_list, s));
+        CUDA_OK(h->d_panel_off.upload(S.panel_off, s)); CUDA_OK(h->d_upd_off.upload(S.upd_off, s));
+        // ---- level plans
+        h->plan.assign(S.nlevels, LevelPlan());
+        std::vector<int32_t> batches; std::vector<int64_t> woff;
+        int64_t wmax = 0;
+        auto add_batch = [&](Batch& b, const std::vector<int32_t>& v, bool large, LevelPlan& P) {
+            b.off = (int32_t)batches.size(); b.cnt = (int32_t)v.size();
+            int64_t w = 0;
+            for (int32_t sn : v) {
+                int nf = S.ns(sn) + S.nr(sn);
+                b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
+                batches.push_back(sn);
+                woff.push_back(large ? w : 0);
+                if (large) w += (int64_t)nf * LNB;
+            }
+            if (large) { P.wtotal = w; wmax = std::max(wmax, w); }
+        };
+        for (int lv = 0; lv < S.nlevels; ++lv) {
+            std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE];
+            for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
+                int32_t sn = S.level_list[q];
+                int nf = S.ns(sn) + S.nr(sn);
+                int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
+                cls[c].push_back(sn);
+                int d = 0; while (nf > kSolveNf[d]) ++d;
+                scl[d].push_back(sn);
+            }
+            LevelPlan& P = h->plan[lv];
+            for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
+            add_batch(P.large, cls[NSMALL], true, P);
+            for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
+        }
+        CUDA_OK(h->d_batches.upload(batches, s)); CUDA_OK(h->d_woff.upload(woff, s));
+        // ---- numeric storage
+        CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
+        CUDA_OK(h->d_U.alloc((size_t)std::max<int64_t>(1, S.upd_total)));
+        CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
+        CUDA_OK(h->d_D.alloc(N)); CUDA_OK(h->d_Dinv.alloc(N));
+        CUDA_OK(h->d_uvec.alloc(std::max<size_t>(1, S.rows.size())));
+        for (DevBuf<double>* b : {&h->d_b, &h->d_x, &h->d_e, &h->d_dx, &h->d_y}) {
+            CUDA_OK(b->alloc(std::max<int64_t>(1, N)));
+            CUDA_OK(cudaMemsetAsync(b->p, 0, std::max<int64_t>(1, N) * sizeof(double), s));
+        }
+        CUDA_OK(h->d_eps.alloc(1)); CUDA_OK(h->d_scal.alloc(4)); CUDA_OK(h->d_nreg.alloc(1));
+        CUDA_OK(cudaMemsetAsync(h->d_eps.p, 0, sizeof(double), s));
+        CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), s));
+        // opt in to large dynamic shared memory for the bigger small-front classes
+        CUDA_OK(cudaFuncSetAttribute(k_factor_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     160 * 160 * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     64 * 64 * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); delete h; return -4; }
+        CUDA_OK(cudaStreamSynchronize(s));
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+void cb200_destroy(cb200_handle* h) {
+    if (!h) return;
+    if (h->stream) { cudaStreamSynchronize(h->stream); }
+    cudaStream_t s = h->stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+}
+
+int32_t cb200_update_values(cb200_handle* h, const int64_t* index, const double* values, int64_t len) {
+    if (len <= 0) return 0;
+    DevBuf<int64_t> di; DevBuf<double> dv;
+    CUDA_OK(di.alloc(len)); CUDA_OK(dv.alloc(len));
+    CUDA_OK(cudaMemcpyAsync(di.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(dv.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, di.p, dv.p, len, h->base);
+    LAUNCH(h);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t cb200_scale_values(cb200_handle* h, const int64_t* index, int64_t len, double scale) {
+    if (len <= 0) return 0;
+    DevBuf<int64_t> di;
+    CUDA_OK(di.alloc(len));
+    CUDA_OK(cudaMemcpyAsync(di.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    k_scale_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, di.p, scale, len, h->base);
+    LAUNCH(h);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int finish_factor(cb200_handle* h) {
+    // success = all(isfinite, Dinv)   (directldl_qdldl.jl:79)
+    CUDA_OK(cudaMemsetAsync(h->d_scal.p + 3, 0, sizeof(unsigned long long), h->stream));
+    if (h->N) { k_absmax<<<std::min(nblk(h->N, 256), 1184), 256, 0, h->stream>>>(h->d_Dinv.p, h->N, h->d_scal.p + 3); LAUNCH(h); }
+    double v[1];
+    int rc = read_scalars(h, v, 3, 1);
+    if (rc) return rc;
+    h->tm.collect();
+    return std::isfinite(v[0]) ? 0 : 1;
+}
+
+int32_t cb200_refactor(cb200_handle* h) {
+    int rc = factor(h, /*static_reg=*/false);
+    if (rc) return rc;
+    return finish_factor(h);
+}
+
+int32_t cb200_solve(cb200_handle* h, double* x, const double* b) {
+    const int64_t N = h->N;
+    if (N == 0) return 0;
+    CUDA_OK(cudaMemcpyAsync(h->d_b.p, b, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = tri_solve(h, h->d_b.p, h->d_x.p);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(x, h->d_x.p, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->tm.collect();
+    return 0;
+}
+
+int32_t cb200_info(const cb200_handle* h, int64_t* nnzA, int64_t* nnzL, int32_t* ngpus) {
+    if (nnzA) *nnzA = h->nnzK;
+    if (nnzL) *nnzL = h->S.nnzL;
+    if (ngpus) *ngpus = 1;
+    return 0;
+}
+
+int32_t cb200_set_maps(cb200_handle* h, int64_t n, int64_t m, int64_t p,
+                       const int64_t* map_P, int64_t nnzP, const int64_t* map_A, int64_t nnzA,
+                       const int64_t* map_Hs, int64_t nHs, const int64_t* map_diag_full,
+                       int64_t ncones, const int32_t* cone_type, const int64_t* cone_dim,
+                       const int64_t* map_soc_u, const int64_t* map_soc_v, const int64_t* map_soc_D) {
+    try {
+        if (n + m + p != h->N) { set_error("cb200_set_maps: n+m+p != N"); return -2; }
+        const int64_t base = h->base;
+        cudaStream_t s = h->stream;
+        h->n = n; h->m = m; h->p = p;
+        auto rebased = [&](const int64_t* src, int64_t len) {
+            std::vector<int64_t> v(len);
+            for (int64_t i = 0; i < len; ++i) v[i] = src[i] - base;
+            return v;
+        };
+        CUDA_OK(h->d_mapP.upload(rebased(map_P, nnzP), s));
+        CUDA_OK(h->d_mapA.upload(rebased(map_A, nnzA), s));
+        std::vector<int64_t> mapHs = rebased(map_Hs, nHs);
+        CUDA_OK(h->d_mapHs.upload(mapHs, s));
+        CUDA_OK(h->d_diagidx.upload(rebased(map_diag_full, h->N), s));
+        h->have_diag = true;
+        // cone tables
+        std::vector<int8_t> dg_kind; std::vector<int32_t> dg_midx, dg_cone; std::vector<int64_t> dg_map;
+        std::vector<int32_t> sd_moff, sd_dim, sd_socid; std::vector<int64_t> sd_hoff;
+        std::vector<int32_t> ex_src, ex_cone, exD_cone;
+        std::vector<int32_t> psd_side; std::vector<int64_t> psd_roff, psd_hoff;
+        int64_t moff = 0, hoff = 0, socrow = 0, roff = 0;
+        int32_t socid = 0;
+        h->psd_maxn = 0;
+        for (int64_t i = 0; i < ncones; ++i) {
+            const int t = cone_type[i];
+            const int64_t d = cone_dim[i];
+            if (t == 0 || t == 1) {
+                for (int64_t k = 0; k < d; ++k) {
+                    dg_kind.push_back((int8_t)t); dg_midx.push_back((int32_t)(moff + k));
+                    dg_cone.push_back(0); dg_map.push_back(mapHs[hoff + k]);
+                }
+                moff += d; hoff += d;
+            } else if (t == 2) {
+                if (d > 4) {
+                    for (int64_t k = 0; k < d; ++k) {
+                        dg_kind.push_back(k == 0 ? 3 : 2); dg_midx.push_back((int32_t)(moff + k));
+                        dg_cone.push_back(socid); dg_map.push_back(mapHs[hoff + k]);
+                        ex_src.push_back((int32_t)(socrow + k)); ex_cone.push_back(socid);
+                    }
+                    exD_cone.push_back(socid);
+                    hoff += d;
+                } else {
+                    sd_moff.push_back((int32_t)moff); sd_dim.push_back((int32_t)d);
+                    sd_socid.push_back(socid); sd_hoff.push_back(hoff);
+                    hoff += d * (d + 1) / 2;
+                }
+                moff += d; socrow += d; socid++;
+            } else if (t == 3) {
+                const int64_t ne = d * (d + 1) / 2;
+                psd_side.push_back((int32_t)d); psd_roff.push_back(roff); psd_hoff.push_back(hoff);
+                roff += d * d; hoff += ne * (ne + 1) / 2; moff += ne;
+                h->psd_maxn = std::max<int32_t>(h->psd_maxn, (int32_t)d);
+            } else { set_error("cb200_set_maps: unsupported cone type"); return -2; }
+        }
+        if (moff != m || hoff != nHs) { set_error("cb200_set_maps: cone table inconsistent with m / nHs"); return -2; }
+        h->ndiag = (int64_t)dg_kind.size();
+        CUDA_OK(h->d_dg_kind.upload(dg_kind, s)); CUDA_OK(h->d_dg_midx.upload(dg_midx, s));
+        CUDA_OK(h->d_dg_cone.upload(dg_cone, s)); CUDA_OK(h->d_dg_map.upload(dg_map, s));
+        h->nsocd = (int32_t)sd_dim.size();
+        CUDA_OK(h->d_sd_moff.upload(sd_moff, s)); CUDA_OK(h->d_sd_dim.upload(sd_dim, s));
+        CUDA_OK(h->d_sd_socid.upload(sd_socid, s)); CUDA_OK(h->d_sd_hoff.upload(sd_hoff, s));
+        h->nexp = (int64_t)ex_src.size(); h->nsocs = (int32_t)exD_cone.size();
+        CUDA_OK(h->d_ex_src.upload(ex_src, s)); CUDA_OK(h->d_ex_cone.upload(ex_cone, s));
+        CUDA_OK(h->d_exD_cone.upload(exD_cone, s));
+        CUDA_OK(h->d_mapu.upload(rebased(map_soc_u, h->nexp), s));
+        CUDA_OK(h->d_mapv.upload(rebased(map_soc_v, h->nexp), s));
+        CUDA_OK(h->d_mapD.upload(rebased(map_soc_D, 2 * (int64_t)h->nsocs), s));
+        h->npsd = (int32_t)psd_side.size(); h->psd_rtotal = roff;
+        CUDA_OK(h->d_psd_side.upload(psd_side, s)); CUDA_OK(h->d_psd_roff.upload(psd_roff, s));
+        CUDA_OK(h->d_psd_hoff.upload(psd_hoff, s));
+        CUDA_OK(h->d_psd_R.alloc(std::max<int64_t>(1, roff))); CUDA_OK(h->d_psd_A.alloc(std::max<int64_t>(1, roff)));
+        h->nsoc = socid; h->nsocrows = socrow;
+        CUDA_OK(h->d_w.alloc(std::max<int64_t>(1, m)));
+        CUDA_OK(h->d_eta.alloc(std::max<int64_t>(1, h->nsoc))); CUDA_OK(h->d_socd.alloc(std::max<int64_t>(1, h->nsoc)));
+        CUDA_OK(h->d_socu.alloc(std::max<int64_t>(1, socrow))); CUDA_OK(h->d_socv.alloc(std::max<int64_t>(1, socrow)));
+        CUDA_OK(h->d_rx.alloc(std::max<int64_t>(1, n))); CUDA_OK(h->d_rz.alloc(std::max<int64_t>(1, m)));
+        if (h->psd_maxn) CUDA_OK(cudaFuncSetAttribute(k_psd_skron, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      std::max(48 * 1024, h->psd_maxn * h->psd_maxn * 8)));
+        CUDA_OK(cudaStreamSynchronize(s));
+        h->maps_set = true;
+        return 0;
+    } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_eta,
+                           const double* soc_d, const double* soc_u, const double* soc_v,
+                           const double* psd_R) {
+    if (!h->maps_set) { set_error("cb200_update_cones: cb200_set_maps not called"); return -2; }
+    cudaStream_t st = h->stream;
+    h->tm.begin(Timers::CONE, st);
+    auto h2d = [&](double* dst, const double* src, int64_t len) -> cudaError_t {
+        if (len <= 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, len * sizeof(double), cudaMemcpyHostToDevice, st);
+    };
+    CUDA_OK(h2d(h->d_w.p, w, h->m));
+    CUDA_OK(h2d(h->d_eta.p, soc_eta, h->nsoc)); CUDA_OK(h2d(h->d_socd.p, soc_d, h->nsoc));
+    CUDA_OK(h2d(h->d_socu.p, soc_u, h->nsocrows)); CUDA_OK(h2d(h->d_socv.p, soc_v, h->nsocrows));
+    CUDA_OK(h2d(h->d_psd_R.p, psd_R, h->psd_rtotal));
+    if (h->ndiag) {
+        k_hs_diag<<<nblk(h->ndiag, 256), 256, 0, st>>>(h->ndiag, h->d_dg_kind.p, h->d_dg_midx.p, h->d_dg_cone.p,
+                                                       h->d_dg_map.p, h->d_w.p, h->d_eta.p, h->d_socd.p, h->d_nz.p);
+        LAUNCH(h);
+    }
+    if (h->nsocd) {
+        k_hs_soc_dense<<<nblk(h->nsocd, 128), 128, 0, st>>>(h->nsocd, h->d_sd_moff.p, h->d_sd_dim.p, h->d_sd_socid.p,
+                                                            h->d_sd_hoff.p, h->d_mapHs.p, h->d_w.p, h->d_eta.p, h->d_nz.p);
+        LAUNCH(h);
+    }
+    if (h->nexp) {
+        k_soc_expansion<<<nblk(h->nexp, 256), 256, 0, st>>>(h->nexp, h->d_ex_src.p, h->d_ex_cone.p, h->d_mapu.p,
+                                                            h->d_mapv.p, h->d_socu.p, h->d_socv.p, h->d_eta.p, h->d_nz.p);
+        k_soc_D<<<nblk(h->nsocs, 128), 128, 0, st>>>(h->nsocs, h->d_exD_cone.p, h->d_mapD.p, h->d_eta.p, h->d_nz.p);
+        h->tm.nlaunch += 2;
+    }
+    if (h->npsd) {
+        k_psd_rrt<<<h->npsd, 256, 0, st>>>(h->d_psd_side.p, h->d_psd_roff.p, h->d_psd_R.p, h->d_psd_A.p);
+        const int ne = h->psd_maxn * (h->psd_maxn + 1) / 2;
+        k_psd_skron<<<dim3(std::max(1, std::min(64, nblk(ne, 8))), h->npsd), 256,
+                      (size_t)h->psd_maxn * h->psd_maxn * sizeof(double), st>>>(
+            h->d_psd_side.p, h->d_psd_roff.p, h->d_psd_hoff.p, h->d_psd_A.p, h->d_mapHs.p, h->d_nz.p);
+        h->tm.nlaunch += 2;
+    }
+    h->tm.end(st);
+    CUDA_OK(cudaGetLastError());
+    int rc = factor(h, /*static_reg=*/true);
+    if (rc) return rc;
+    return finish_factor(h);
+}
+
+int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
+                       double* lhsx, double* lhsz, int32_t* ir_rounds) {
+    if (!h->maps_set) { set_error("cb200_solve_ir: cb200_set_maps not called"); return -2; }
+    cudaStream_t st = h->stream;
+    const int64_t N = h->N, n = h->n, m = h->m;
+    if (ir_rounds) *ir_rounds = 0;
+    if (N == 0) return 0;
+    if (n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_build_rhs<<<nblk(N, 256), 256, 0, st>>>(h->d_rx.p, h->d_rz.p, n, m, N, h->d_b.p);
+    CUDA_OK(cudaMemsetAsync(h->d_scal.p + 1, 0, sizeof(unsigned long long), st));
+    k_absmax<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(h->d_b.p, N, h->d_scal.p + 1);
+    h->tm.nlaunch += 2;
+    double* x = h->d_x.p; double* dx = h->d_dx.p; double* e = h->d_e.p;
+    int rc = tri_solve(h, h->d_b.p, x);
+    if (rc) return rc;
+    int ok = 1;
+    if (h->st.iterative_refinement_enable) {
+        // _iterative_refinement (kktsolver_directldl.jl:389-449)
+        rc = residual(h, x, e, 2); if (rc) return rc;
+        double sc[2];
+        rc = read_scalars(h, sc, 1, 2); if (rc) return rc;
+        const double normb = sc[0];
+        double norme = sc[1];
+        if (!std::isfinite(norme)) ok = 0;
+        for (int i = 0; ok && i < h->st.iterative_refinement_max_iter; ++i) {
+            if (norme <= h->st.iterative_refinement_abstol + h->st.iterative_refinement_reltol * normb) break;
+            const double lastnorme = norme;
+            rc = tri_solve(h, e, dx); if (rc) return rc;
+            k_axpy1<<<nblk(N, 256), 256, 0, st>>>(dx, x, N); LAUNCH(h);
+            rc = residual(h, dx, e, 2); if (rc) return rc;
+            rc = read_scalars(h, sc, 2, 1); if (rc) return rc;
+            norme = sc[0];
+            if (ir_rounds) (*ir_rounds)++;
+            if (!std::isfinite(norme)) { ok = 0; break; }
+            const double ratio = lastnorme / norme;
+            if (ratio < h->st.iterative_refinement_stop_ratio) {
+                if (ratio > 1.0) std::swap(x, dx);
+                break;
+            }
+            std::swap(x, dx);
+        }
+    } else {
+        CUDA_OK(cudaMemsetAsync(h->d_scal.p + 2, 0, sizeof(unsigned long long), st));
+        k_absmax<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(x, N, h->d_scal.p + 2); LAUNCH(h);
+        double sc[1];
+        rc = read_scalars(h, sc, 2, 1); if (rc) return rc;
+        ok = std::isfinite(sc[0]);
+    }
+    // keep handle buffers consistent with the pointer swaps (kktsolver_directldl.jl:445)
+    if (x != h->d_x.p) std::swap(h->d_x.p, h->d_dx.p);
+    if (ok) {
+        if (lhsx && n) CUDA_OK(cudaMemcpyAsync(lhsx, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (lhsz && m) CUDA_OK(cudaMemcpyAsync(lhsz, h->d_x.p + n, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    h->tm.collect();
+    return ok ? 0 : 1;
+}
+
+static int32_t update_block(cb200_handle* h, const DevBuf<int64_t>& map, const double* values, int64_t len) {
+    if (!h->maps_set) { set_error("cb200_update_P/A: cb200_set_maps not called"); return -2; }
+    if ((int64_t)map.n != len) { set_error("cb200_update_P/A: length mismatch"); return -2; }
+    if (len == 0) return 0;
+    DevBuf<double> dv;
+    CUDA_OK(dv.alloc(len));
+    CUDA_OK(cudaMemcpyAsync(dv.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, map.p, dv.p, len, 0);
+    LAUNCH(h);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int32_t cb200_update_P(cb200_handle* h, const double* values, int64_t len) { return update_block(h, h->d_mapP, values, len); }
+int32_t cb200_update_A(cb200_handle* h, const double* values, int64_t len) { return update_block(h, h->d_mapA, values, len); }
+
+int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len) {
+    cudaStream_t st = h->stream;
+    const double* src = nullptr; int64_t n = 0;
+    switch (what) {
+        case 0: src = h->d_nz.p; n = h->nnzK; break;
+        case 1: src = h->d_D.p; n = h->N; break;
+        case 2: src = h->d_L.p; n = (int64_t)h->d_L.n; break;
+        case 3: { if (len != h->N) { set_error("download: length"); return -2; }
+                  for (int64_t i = 0; i < len; ++i) out[i] = (double)h->S.perm[i]; return 0; }
+        case 4: src = h->d_eps.p; n = 1; break;
+        case 5: { if (len != 1) { set_error("download: length"); return -2; }
+                  unsigned int v = 0;
+                  CUDA_OK(cudaMemcpyAsync(&v, h->d_nreg.p, sizeof(v), cudaMemcpyDeviceToHost, st));
+                  CUDA_OK(cudaStreamSynchronize(st)); out[0] = (double)v; return 0; }
+        default: set_error("download: bad selector"); return -2;
+    }
+    if (len != n) { set_error("download: length mismatch"); return -2; }
+    if (n) CUDA_OK(cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len) {
+    double v[7] = {h->tm.ms[0], h->tm.ms[1], h->tm.ms[2], h->tm.ms[3], h->tm.nfactor, h->tm.nsolve, h->tm.nlaunch};
+    for (int i = 0; i < len && i < 7; ++i) out[i] = v[i];
+    return 0;
+}
+int32_t cb200_reset_timers(cb200_handle* h) {
+    for (double& x : h->tm.ms) x = 0;
+    h->tm.nfactor = h->tm.nsolve = h->tm.nlaunch = 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Supernodal multifrontal symbolic analysis (see symbolic.h).
+#include "symbolic.h"
+#include "ordering.h"
+
+#include <algorithm>
+#include <numeric>
+#include <cstring>
+#include <stdexcept>
+
+namespace cb200 {
+
+namespace {
+
+// Elimination tree of the permuted matrix given its *upper* pattern by columns
+// (Liu's algorithm with path compression).
+void etree_upper(int32_t n, const std::vector<int64_t>& up, const std::vector<int32_t>& ui,
+                 std::vector<int32_t>& parent) {
+    parent.assign(n, -1);
+    std::vector<int32_t> anc(n, -1);
+    for (int32_t j = 0; j < n; ++j)
+        for (int64_t p = up[j]; p < up[j + 1]; ++p) {
+            int32_t i = ui[p];
+            while (i != -1 && i < j) {
+                int32_t nx = anc[i];
+                anc[i] = j;
+                if (nx == -1) parent[i] = j;
+                i = nx;
+            }
+        }
+}
+
+}  // namespace
+
+void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
+                      const SymbolicOptions& opt, const int64_t* user_perm, Symbolic& S) {
+    if (N64 > 2000000000LL) throw std::runtime_error("N too large for int32 indices");
+    const int32_t N = (int32_t)N64;
+    const int64_t nnzK = colptr[N];
+    S.N = N; S.nnzK = nnzK;
+
+    // ---------------------------------------------------------------- 1. fill-reducing order
+    std::vector<int32_t> p0(N);
+    if (user_perm) {
+        for (int32_t i = 0; i < N; ++i) p0[i] = (int32_t)user_perm[i];
+    } else if (opt.ordering == 2) {
+        std::iota(p0.begin(), p0.end(), 0);
+    } else {
+        std::vector<int64_t> xadj; std::vector<int32_t> adj;
+        build_sym_graph(N, colptr, rowval, xadj, adj);
+        if (opt.ordering == 0) amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
+        else nd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, p0.data());
+    }
+    std::vector<int32_t> ip0(N);
+    for (int32_t k = 0; k < N; ++k) ip0[p0[k]] = k;
+
+    // permuted pattern as upper-by-column (row < col) == lower-by-row; also lower-by-column
+    auto build_patterns = [&](const std::vector<int32_t>& ip, std::vector<int64_t>& up,
+                              std::vector<int32_t>& ui, std::vector<int64_t>& lp,
+                              std::vector<int32_t>& li) {
+        up.assign(N + 1, 0); lp.assign(N + 1, 0);
+        for (int32_t j = 0; j < N; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t a = ip[rowval[p]], b = ip[j];
+                if (a == b) continue;
+                int32_t lo = std::min(a, b), hi = std::max(a, b);
+                up[hi + 1]++; lp[lo + 1]++;
+            }
+        for (int32_t j = 0; j < N; ++j) { up[j + 1] += up[j]; lp[j + 1] += lp[j]; }
+        ui.resize(up[N]); li.resize(lp[N]);
+        std::vector<int64_t> pu(up.begin(), up.end() - 1), pl(lp.begin(), lp.end() - 1);
+        for (int32_t j = 0; j < N; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t a = ip[rowval[p]], b = ip[j];
+                if (a == b) continue;
+                int32_t lo = std::min(a, b), hi = std::max(a, b);
+                ui[pu[hi]++] = lo; li[pl[lo]++] = hi;
+            }
+    };
+    std::vector<int64_t> up, lp; std::vector<int32_t> ui, li;
+    build_patterns(ip0, up, ui, lp, li);
+
+    // ---------------------------------------------------------------- 2. etree + column counts
+    std::vector<int32_t> parent;
+    etree_upper(N, up, ui, parent);
+    std::vector<int32_t> cptr(N + 1, 0), clist(N);
+    auto build_children = [&](const std::vector<int32_t>& par) {
+        std::fill(cptr.begin(), cptr.end(), 0);
+        for (int32_t j = 0; j < N; ++j) if (par[j] >= 0) cptr[par[j] + 1]++;
+        for (int32_t j = 0; j < N; ++j) cptr[j + 1] += cptr[j];
+        std::vector<int32_t> pos(cptr.begin(), cptr.end() - 1);
+        for (int32_t j = 0; j < N; ++j) if (par[j] >= 0) clist[pos[par[j]]++] = j;
+    };
+    build_children(parent);
+    // column structures by list merging (children are always numbered below their parent)
+    std::vector<int32_t> count(N, 0);
+    {
+        std::vector<std::vector<int32_t>> lists(N);
+        std::vector<int32_t> mark(N, -1);
+        for (int32_t j = 0; j < N; ++j) {
+            auto& L = lists[j];
+            mark[j] = j;
+            for (int64_t p = lp[j]; p < lp[j + 1]; ++p) {
+                int32_t i = li[p];
+                if (mark[i] != j) { mark[i] = j; L.push_back(i); }
+            }
+            for (int32_t q = cptr[j]; q < cptr[j + 1]; ++q) {
+                auto& C = lists[clist[q]];
+                for (int32_t i : C) if (mark[i] != j) { mark[i] = j; L.push_back(i); }
+                std::vector<int32_t>().swap(C);
+            }
+            count[j] = (int32_t)L.size();
+            if (parent[j] < 0) std::vector<int32_t>().swap(L);
+        }
+    }
+
+    // ---------------------------------------------------------------- 3. postorder (big child last)
+    std::vector<int32_t> post(N), ipost(N);
+    {
+        // sort each child list by count ascending so the heaviest child is visited last
+        for (int32_t j = 0; j < N; ++j)
+            std::sort(clist.begin() + cptr[j], clist.begin() + cptr[j + 1],
+                      [&](int32_t a, int32_t b) { return count[a] < count[b] || (count[a] == count[b] && a < b); });
+        std::vector<int32_t> stack, it(N, 0);
+        int32_t k = 0;
+        for (int32_t r = 0; r < N; ++r) {
+            if (parent[r] >= 0) continue;
+            stack.push_back(r);
+            while (!stack.empty()) {
+                int32_t v = stack.back();
+                if (cptr[v] + it[v] < cptr[v + 1]) { stack.push_back(clist[cptr[v] + it[v]++]); }
+                else { post[k++] = v; stack.pop_back(); }
+            }
+        }
+        for (int32_t q = 0; q < N; ++q) ipost[post[q]] = q;
+    }
+    S.perm.resize(N); S.iperm.resize(N);
+    for (int32_t q = 0; q < N; ++q) S.perm[q] = p0[post[q]];
+    for (int32_t q = 0; q < N; ++q) S.iperm[S.perm[q]] = q;
+    {   // relabel parent / count into postorder
+        std::vector<int32_t> par2(N), cnt2(N);
+        for (int32_t q = 0; q < N; ++q) {
+            int32_t v = post[q];
+            par2[q] = parent[v] >= 0 ? ipost[parent[v]] : -1;
+            cnt2[q] = count[v];
+        }
+        parent.swap(par2); count.swap(cnt2);
+    }
+    build_patterns(S.iperm, up, ui, lp, li);
+    std::vector<int64_t>().swap(up); std::vector<int32_t>().swap(ui);
+
+    // ---------------------------------------------------------------- 4. maximal supernodes
+    std::vector<int32_t> first;      // first column of each (fundamental/maximal) supernode
+    first.push_back(0);
+    for (int32_t j = 1; j < N; ++j)
+        if (!(parent[j - 1] == j && count[j - 1] == count[j] + 1)) first.push_back(j);
+    int32_t nsn = (int32_t)first.size();
+    if (N == 0) { nsn = 0; first.clear(); }
+    first.push_back(N);
+    std::vector<int32_t> snof(N);
+    for (int32_t s = 0; s < nsn; ++s) for (int32_t j = first[s]; j < first[s + 1]; ++j) snof[j] = s;
+    // supernodal tree
+    std::vector<int32_t> spar(nsn, -1);
+    for (int32_t s = 0; s < nsn; ++s) {
+        int32_t last = first[s + 1] - 1;
+        spar[s] = parent[last] >= 0 ? snof[parent[last]] : -1;
+    }
+    // ---------------------------------------------------------------- 5. relaxed amalgamation
+    // Merge supernode c into its parent p when c is p's immediately preceding sibling-free
+    // neighbour in postorder (first[c+1] == first[p]) and the padding zeros stay small.
+    std::vector<int32_t> merged_into(nsn, -1);         // c -> p
+    {
+        std::vector<int64_t> zeros(nsn, 0);
+        std::vector<int32_t> width(nsn), below(nsn), head(nsn);   // head: first column after merges
+        for (int32_t s = 0; s < nsn; ++s) {
+            width[s] = first[s + 1] - first[s];
+            below[s] = count[first[s + 1] - 1];      // rows below the supernode's last column
+            head[s] = first[s];
+        }
+        for (int32_t p = 0; p < nsn; ++p) {
+            // candidate: the supernode ending right before head[p] whose parent is p
+            while (true) {
+                if (head[p] == 0) break;
+                int32_t c = snof[head[p] - 1];
+                while (merged_into[c] >= 0) c = merged_into[c];   // representative (never p itself)
+                if (c == p || spar[c] != p) break;
+                int32_t wc = width[c], wp = width[p];
+                int32_t w = wc + wp;
+                if (w > opt.max_width) break;
+                int64_t newz = (int64_t)wc * ((int64_t)wp + below[p] - below[c]);
+                int64_t z = zeros[c] + zeros[p] + newz;
+                double total = (double)w * (w + 1) / 2.0 + (double)w * below[p];
+                double frac = (double)z / total;
+                bool ok = (w <= opt.relax_small) ||
+                          (w <= 32 && frac < opt.relax_z1) ||
+                          (w <= 96 && frac < opt.relax_z2) || (frac < opt.relax_z3);
+                if (!ok) break;
+                merged_into[c] = p;
+                zeros[p] = z; width[p] = w; head[p] = head[c];
+                // c's children now hang off p
+            }
+        }
+    }
+    // final supernodes: survivors, with their merged column ranges
+    std::vector<int32_t> rep(nsn);
+    for (int32_t s = 0; s < nsn; ++s) {
+        int32_t r = s;
+        while (merged_into[r] >= 0) r = merged_into[r];
+        rep[s] = r;
+    }
+    std::vector<int32_t> newid(nsn, -1);
+    S.sn_first.clear();
+    int32_t ns2 = 0;
+    for (int32_t s = 0; s < nsn; ++s) {
+        // a merged group is contiguous and ends with its representative; its first member is
+        // the first s with rep[s] == r
+        if (s == 0 || rep[s] != rep[s - 1]) { S.sn_first.push_back(first[s]); newid[rep[s]] = ns2++; }
+    }
+    S.sn_first.push_back(N);
+    S.nsuper = ns2;
+    S.sn_of_col.resize(N);
+    for (int32_t s = 0; s < ns2; ++s)
+        for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1]; ++j) S.sn_of_col[j] = s;
+    S.sn_parent.assign(ns2, -1);
+    for (int32_t s = 0; s < ns2; ++s) {
+        int32_t last = S.sn_first[s + 1] - 1;
+        S.sn_parent[s] = parent[last] >= 0 ? S.sn_of_col[parent[last]] : -1;
+    }
+    S.child_ptr.assign(ns2 + 1, 0);
+    for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_ptr[S.sn_parent[s] + 1]++;
+    for (int32_t s = 0; s < ns2; ++s) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_list.resize(S.child_ptr[ns2]);
+    {
+        std::vector<int32_t> pos(S.child_ptr.begin(), S.child_ptr.end() - 1);
+        for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_list[pos[S.sn_parent[s]]++] = s;
+    }
+
+    // ---------------------------------------------------------------- 6. supernodal row structures
+    S.rows_ptr.assign(ns2 + 1, 0);
+    {
+        std::vector<std::vector<int32_t>> R(ns2);
+        std::vector<int32_t> mark(N, -1);
+        for (int32_t s = 0; s < ns2; ++s) {
+            int32_t f = S.sn_first[s], l = S.sn_first[s + 1] - 1;
+            auto& L = R[s];
+            for (int32_t j = f; j <= l; ++j)
+                for (int64_t p = lp[j]; p < lp[j + 1]; ++p) {
+                    int32_t i = li[p];
+                    if (i > l && mark[i] != s) { mark[i] = s; L.push_back(i); }
+                }
+            for (int32_t q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q)
+                for (int32_t i : R[S.child_list[q]])
+                    if (i > l && mark[i] != s) { mark[i] = s; L.push_back(i); }
+            std::sort(L.begin(), L.end());
+            S.rows_ptr[s + 1] = S.rows_ptr[s] + (int64_t)L.size();
+        }
+        S.rows.resize(S.rows_ptr[ns2]);
+        for (int32_t s = 0; s < ns2; ++s)
+            std::copy(R[s].begin(), R[s].end(), S.rows.begin() + S.rows_ptr[s]);
+    }
+    // parent consistency: the assembly parent must own the first below-row
+    for (int32_t s = 0; s < ns2; ++s) {
+        if (S.nr(s) > 0) {
+            int32_t ps = S.sn_of_col[S.rows[S.rows_ptr[s]]];
+            if (ps != S.sn_parent[s]) S.sn_parent[s] = ps;   // (amalgamation keeps this equal)
+        } else S.sn_parent[s] = -1;
+    }
+    // rebuild children in case the loop above changed anything
+    std::fill(S.child_ptr.begin(), S.child_ptr.end(), 0);
+    for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_ptr[S.sn_parent[s] + 1]++;
+    for (int32_t s = 0; s < ns2; ++s) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_list.resize(S.child_ptr[ns2]);
+    {
+        std::vector<int32_t> pos(S.child_ptr.begin(), S.child_ptr.end() - 1);
+        for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_list[pos[S.sn_parent[s]]++] = s;
+    }
+
+    // ---------------------------------------------------------------- 7. storage + maps
+    S.panel_off.assign(ns2 + 1, 0); S.upd_off.assign(ns2 + 1, 0);
+    S.nnzL = 0; S.flops = 0; S.max_front = 0; S.max_width = 0;
+    for (int32_t s = 0; s < ns2; ++s) {
+        int64_t w = S.ns(s), r = S.nr(s), nf = w + r;
+        S.panel_off[s + 1] = S.panel_off[s] + nf * w;
+        S.upd_off[s + 1] = S.upd_off[s] + r * r;
+        S.nnzL += w * (w - 1) / 2 + w * r;
+        for (int64_t k = 0; k < w; ++k) { double c = (double)(nf - k); S.flops += c * c; }
+        S.max_front = std::max<int32_t>(S.max_front, (int32_t)nf);
+        S.max_width = std::max<int32_t>(S.max_width, (int32_t)w);
+    }
+    S.upd_total = S.upd_off[ns2];
+    // relative indices of R_s in the parent's front
+    S.rel.resize(S.rows.size());
+    for (int32_t s = 0; s < ns2; ++s) {
+        int32_t p = S.sn_parent[s];
+        if (p < 0) continue;
+        int32_t pf = S.sn_first[p], pl = S.sn_first[p + 1] - 1, pw = pl - pf + 1;
+        const int32_t* PR = S.rows.data() + S.rows_ptr[p];
+        int32_t pnr = S.nr(p);
+        int32_t cur = 0;
+        for (int64_t q = S.rows_ptr[s]; q < S.rows_ptr[s + 1]; ++q) {
+            int32_t r = S.rows[q];
+            if (r <= pl) { S.rel[q] = r - pf; }
+            else {
+                while (cur < pnr && PR[cur] < r) cur++;
+                if (cur >= pnr || PR[cur] != r) throw std::runtime_error("symbolic: child row not in parent front");
+                S.rel[q] = pw + cur;
+            }
+        }
+    }
+    // scatter map of the original K entries into the panels
+    S.a_map.resize(nnzK);
+    for (int32_t j = 0; j < N; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t a = S.iperm[rowval[p]], b = S.iperm[j];
+            int32_t c = std::min(a, b), r = std::max(a, b);
+            int32_t s = S.sn_of_col[c];
+            int32_t f = S.sn_first[s], l = S.sn_first[s + 1] - 1, w = l - f + 1;
+            int64_t nf = w + S.nr(s);
+            int64_t lr;
+            if (r <= l) lr = r - f;
+            else {
+                const int32_t* Rb = S.rows.data() + S.rows_ptr[s];
+                const int32_t* Re = Rb + S.nr(s);
+                const int32_t* it = std::lower_bound(Rb, Re, r);
+                if (it == Re || *it != r) throw std::runtime_error("symbolic: K entry outside front");
+                lr = w + (it - Rb);
+            }
+            S.a_map[p] = S.panel_off[s] + (int64_t)(c - f) * nf + lr;
+        }
+
+    // ---------------------------------------------------------------- 8. level sets
+    S.sn_level.assign(ns2, 0);
+    int32_t nl = 0;
+    for (int32_t s = 0; s < ns2; ++s) {          // children precede parents
+        int32_t p = S.sn_parent[s];
+        if (p >= 0) S.sn_level[p] = std::max(S.sn_level[p], S.sn_level[s] + 1);
+        nl = std::max(nl, S.sn_level[s] + 1);
+    }
+    S.nlevels = nl;
+    S.level_ptr.assign(nl + 1, 0);
+    for (int32_t s = 0; s < ns2; ++s) S.level_ptr[S.sn_level[s] + 1]++;
+    for (int32_t l = 0; l < nl; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
+    S.level_list.resize(ns2);
+    {
+        std::vector<int32_t> pos(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        for (int32_t s = 0; s < ns2; ++s) S.level_list[pos[S.sn_level[s]]++] = s;
+    }
+}
+
+}  // namespace cb200

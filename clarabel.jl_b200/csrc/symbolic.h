@@ -1,0 +1,55 @@
+// Supernodal multifrontal symbolic analysis of the permuted KKT pattern (host, setup-time).
+// Replaces the symbolic half of QDLDL.qdldl(...; logical=true) at the reference call site
+// src/kktsolvers/direct-ldl/directldl_qdldl.jl:18-25 (F0 in SURVEY.md section 8a): ordering,
+// elimination tree, supernodes, front structures, assembly (extend-add) maps, level sets.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace cb200 {
+
+struct SymbolicOptions {
+    int32_t ordering = 1;        // 0 = AMD, 1 = nested dissection over AMD leaves, 2 = natural
+    double dense_scale = 1.5;    // AMD dense-row threshold multiplier (reference uses 1.5)
+    int32_t nd_leaf = 96;        // ND leaf size
+    int32_t relax_small = 8;     // always merge a last child when merged width <= this
+    double relax_z1 = 0.50;      // allowed zero fraction for merged width <= 32
+    double relax_z2 = 0.20;      // ... <= 96
+    double relax_z3 = 0.05;      // otherwise
+    int32_t max_width = 512;     // never merge beyond this many pivot columns
+};
+
+struct Symbolic {
+    int64_t N = 0, nnzK = 0;
+    std::vector<int32_t> perm;      // perm[k]  = original index of permuted position k
+    std::vector<int32_t> iperm;     // iperm[i] = permuted position of original index i
+    int32_t nsuper = 0;
+    std::vector<int32_t> sn_first;  // [nsuper+1] first permuted column of each supernode
+    std::vector<int32_t> sn_of_col; // [N]
+    std::vector<int64_t> rows_ptr;  // [nsuper+1] into rows / rel
+    std::vector<int32_t> rows;      // below-block row indices R_s (permuted, ascending)
+    std::vector<int32_t> rel;       // position of R_s[i] inside the parent's front
+    std::vector<int32_t> sn_parent; // [nsuper] assembly-tree parent (-1 = root)
+    std::vector<int32_t> child_ptr; // [nsuper+1]
+    std::vector<int32_t> child_list;
+    std::vector<int64_t> panel_off; // [nsuper+1] doubles; panel s is nf x ns column-major, ld = nf
+    std::vector<int64_t> upd_off;   // [nsuper+1] doubles; update block s is nr x nr, ld = nr
+    std::vector<int64_t> a_map;     // [nnzK] K nz (original order) -> offset in panel storage
+    std::vector<int32_t> sn_level;  // [nsuper]
+    int32_t nlevels = 0;
+    std::vector<int32_t> level_ptr; // [nlevels+1]
+    std::vector<int32_t> level_list;// supernodes grouped by level (ascending size inside level)
+    int64_t nnzL = 0;               // strictly-lower entries of L incl. amalgamation zeros
+    double flops = 0;               // sum over pivot columns of (col length incl. diag)^2
+    int64_t upd_total = 0;          // doubles in update storage
+    int32_t max_front = 0, max_width = 0;
+    inline int32_t ns(int32_t s) const { return sn_first[s + 1] - sn_first[s]; }
+    inline int32_t nr(int32_t s) const { return (int32_t)(rows_ptr[s + 1] - rows_ptr[s]); }
+};
+
+// colptr/rowval: upper-triangular CSC pattern (0-based) of the N x N KKT matrix.
+// user_perm (optional, length N): use this ordering instead of computing one.
+void symbolic_analyze(int64_t N, const int64_t* colptr, const int64_t* rowval,
+                      const SymbolicOptions& opt, const int64_t* user_perm, Symbolic& S);
+
+}  // namespace cb200

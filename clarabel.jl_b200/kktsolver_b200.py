@@ -1,0 +1,165 @@
+"""`B200KKTSolver`: the AbstractKKTSolver implementation over the C-ABI.
+
+Mirrors the 6-method interface of src/kktsolvers/kktsolver_defaults.jl:1-47 and the constructor
+signature `DirectLDLKKTSolver{T}(P, A, cones, m, n, settings)` (kktsolver_directldl.jl:46-52).
+Assembly of the KKT pattern and of the index maps stays on the host (setup-time, as in the
+reference); everything per-iteration runs on the device:
+
+    update(cones)  -> cb200_update_cones   (H2D of the NT scaling state, G1/G2 value update,
+                                            G3 static regularisation, G4-G6 factorisation)
+    setrhs + solve -> cb200_solve_ir       (G7 triangular solves, G8 residuals, IR loop)
+
+`B200DirectLDLSolver` below is the INNER boundary (AbstractDirectLDLSolver, the reference's own
+plugin registry: directldl_defaults.jl:1-72), kept so that the stock DirectLDLKKTSolver logic
+(oracle/kktsolver_oracle.py in this repo's tests) can drive the device factorisation through
+update_values!/scale_values!/refactor!/solve! exactly as it drives QDLDL.
+"""
+import ctypes as C
+import numpy as np
+
+from . import lib as _lib
+from .kkt_assembly import assemble_kkt_matrix, fill_Dsigns
+from .kktsystem import register_kktsolver
+
+
+class LinearSolverInfo:
+    """LinearSolverInfo(name, threads, direct, nnzA, nnzL)  (src/types.jl:198-206)."""
+    def __init__(self, name, threads, direct, nnzA, nnzL):
+        self.name, self.threads, self.direct, self.nnzA, self.nnzL = name, threads, direct, nnzA, nnzL
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class B200DirectLDLSolver:
+    """INNER boundary: ldlsolver_constructor(::Val{:b200}), ldlsolver_matrix_shape = :triu."""
+    matrix_shape = "triu"
+
+    def __init__(self, KKT, Dsigns, settings, **cs_over):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        cs = _lib.make_settings(settings, **cs_over)
+        self._keep = (_i64(KKT.indptr), _i64(KKT.indices), _c64(KKT.data), _i64(Dsigns))
+        cp, ri, nz, ds = self._keep
+        _lib.check(self._L.cb200_create(KKT.shape[0], _p(cp), _p(ri), _p(nz), _p(ds), C.byref(cs),
+                                        C.byref(self._h)), "cb200_create")
+        self.N = KKT.shape[0]
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.cb200_destroy(self._h); self._h = None
+        except Exception:
+            pass
+
+    def update_values(self, index, values):
+        index, values = _i64(index), _c64(values)
+        _lib.check(self._L.cb200_update_values(self._h, _p(index), _p(values), len(index)),
+                   "cb200_update_values")
+
+    def scale_values(self, index, scale):
+        index = _i64(index)
+        _lib.check(self._L.cb200_scale_values(self._h, _p(index), len(index), float(scale)),
+                   "cb200_scale_values")
+
+    def refactor(self):
+        return _lib.check(self._L.cb200_refactor(self._h), "cb200_refactor")
+
+    def solve(self, x, b=None):
+        """solve!(s, KKT, x, b); with b=None solves in place (QDLDL.jl convention)."""
+        bb = _c64(x.copy() if b is None else b)
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        _lib.check(self._L.cb200_solve(self._h, _p(x), _p(bb)), "cb200_solve")
+
+    def info(self):
+        a, l, g = C.c_int64(), C.c_int64(), C.c_int32()
+        self._L.cb200_info(self._h, C.byref(a), C.byref(l), C.byref(g))
+        return LinearSolverInfo("b200", g.value, True, a.value, l.value)
+
+    linear_solver_info = info
+
+    def download(self, what, n):
+        out = np.empty(n)
+        _lib.check(self._L.cb200_download(self._h, what, _p(out), n), "cb200_download")
+        return out
+
+    def timers(self):
+        out = np.zeros(7)
+        self._L.cb200_get_timers(self._h, _p(out), 7)
+        return dict(cone_ms=out[0], factor_ms=out[1], solve_ms=out[2], spmv_ms=out[3],
+                    nfactor=int(out[4]), nsolve=int(out[5]), nlaunch=int(out[6]))
+
+    def reset_timers(self):
+        self._L.cb200_reset_timers(self._h)
+
+
+class B200KKTSolver:
+    """OUTER boundary: AbstractKKTSolver over the fused C-ABI entry points."""
+
+    def __init__(self, P, A, cones, m, n, settings, **cs_over):
+        self.m, self.n = m, n
+        self.settings = settings
+        self.KKT, self.map = assemble_kkt_matrix(P, A, cones)
+        self.p = cones.p
+        self.Dsigns = fill_Dsigns(m, n, self.p)
+        self.ldl = B200DirectLDLSolver(self.KKT, self.Dsigns, settings, **cs_over)
+        L, h = self.ldl._L, self.ldl._h
+        mp = self.map
+        ctype = np.ascontiguousarray(cones.types, dtype=np.int32)
+        cdim = _i64(cones.dims)
+        self._maps = [_i64(mp.P), _i64(mp.A), _i64(mp.Hsblocks), _i64(mp.diag_full),
+                      _i64(mp.soc_u), _i64(mp.soc_v), _i64(mp.soc_D)]
+        mP, mA, mH, mD, mu, mv, mDD = self._maps
+        _lib.check(L.cb200_set_maps(h, n, m, self.p, _p(mP), len(mP), _p(mA), len(mA), _p(mH), len(mH),
+                                    _p(mD), len(ctype), _p(ctype), _p(cdim), _p(mu), _p(mv), _p(mDD)),
+                   "cb200_set_maps")
+        self._rx = np.zeros(n); self._rz = np.zeros(m)
+        self.ir_rounds = 0; self.n_solves = 0
+
+    def linear_solver_info(self):
+        return self.ldl.info()
+
+    def update(self, cones):
+        st = cones.export_state()
+        arrs = [_c64(st[k]) for k in ("w", "soc_eta", "soc_d", "soc_u", "soc_v", "psd_R")]
+        return _lib.check(self.ldl._L.cb200_update_cones(self.ldl._h, *[_p(a) for a in arrs]),
+                          "cb200_update_cones")
+
+    def setrhs(self, rhsx, rhsz):
+        self._rx[:] = rhsx
+        self._rz[:] = rhsz
+
+    def solve(self, lhsx, lhsz):
+        if lhsx is not None:
+            assert lhsx.dtype == np.float64 and lhsx.flags.c_contiguous
+        if lhsz is not None:
+            assert lhsz.dtype == np.float64 and lhsz.flags.c_contiguous
+        rounds = C.c_int32(0)
+        ok = _lib.check(self.ldl._L.cb200_solve_ir(self.ldl._h, _p(self._rx), _p(self._rz),
+                                                   _p(lhsx), _p(lhsz), C.byref(rounds)),
+                        "cb200_solve_ir")
+        self.ir_rounds += rounds.value; self.n_solves += 1
+        return ok
+
+    def update_P(self, P):
+        v = _c64(P.data)
+        _lib.check(self.ldl._L.cb200_update_P(self.ldl._h, _p(v), len(v)), "cb200_update_P")
+
+    def update_A(self, A):
+        v = _c64(A.data)
+        _lib.check(self.ldl._L.cb200_update_A(self.ldl._h, _p(v), len(v)), "cb200_update_A")
+
+    def device_nzval(self):
+        return self.ldl.download(0, self.KKT.nnz)
+
+
+register_kktsolver("b200", B200KKTSolver)

@@ -1,0 +1,74 @@
+"""CPU: the product's host-side symbolic analysis (ordering, supernodes, a_map / rel maps, level
+sets) checked by running a numpy emulation of the multifrontal numeric phase on those maps and
+comparing with the QDLDL oracle and scipy's SuperLU; plus the C-ABI export check."""
+import ctypes
+import numpy as np
+import scipy.sparse.linalg as spl
+import pytest
+from common import small_instances, kkt_fixture, sym_full
+from mf_numpy import MFNumpy
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import re, os
+    from clarabel_jl_b200 import lib
+    L = lib.lib()
+    hdr = open(os.path.join(os.path.dirname(lib.LIB_PATH), "..", "include", "clarabel_b200.h")).read()
+    declared = set(re.findall(r"\b(cb200_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert declared == set(lib.EXPORTED)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_no_cuda_device_fails_loudly(cb, gpu_available):
+    if gpu_available:
+        pytest.skip("GPU present")
+    from clarabel_jl_b200.kktsolver_b200 import B200DirectLDLSolver
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, small_instances(cb)["C1s"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200DirectLDLSolver(KKT, Ds, cb.Settings())
+
+
+@pytest.mark.parametrize("name", ["C1s", "C2s", "C3s", "C4s", "C5s"])
+@pytest.mark.parametrize("ordering", [0, 1])
+def test_symbolic_maps_via_numpy_multifrontal(cb, name, ordering):
+    from clarabel_jl_b200 import lib
+    from oracle import qdldl as oq
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, small_instances(cb)[name])
+    N = KKT.shape[0]
+    S = lib.Symbolic(KKT, ordering=ordering, nd_leaf=32)
+    a = S.arrays()
+    assert sorted(a["perm"].tolist()) == list(range(N))
+    # supernode partition and tree sanity
+    assert a["sn_first"][0] == 0 and a["sn_first"][-1] == N and np.all(np.diff(a["sn_first"]) > 0)
+    par = a["sn_parent"]
+    assert np.all((par == -1) | (par > np.arange(len(par))))
+    assert np.all(a["sn_level"][par[par >= 0]] > a["sn_level"][par >= 0])
+    mf = MFNumpy(a)
+    D = mf.factor(KKT.data, Ds)
+    assert np.all(np.sign(D) == Ds[a["perm"]])          # quasidefinite => signs as expected
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(N)
+    x = mf.solve(b)
+    Kf = sym_full(KKT)
+    assert np.abs(Kf @ x - b).max() < 1e-9 * max(1.0, np.abs(x).max())
+    # same system through the QDLDL oracle and SuperLU
+    F = oq.QDLDLFactorisation(KKT, Ds)
+    assert F.refactor()
+    xo = b.copy(); F.solve(xo)
+    xs = spl.splu(Kf).solve(b)
+    scale = max(1.0, np.abs(xs).max())
+    assert np.abs(x - xo).max() < 1e-8 * scale and np.abs(xo - xs).max() < 1e-8 * scale
+    # the factorisation's inertia matches between engines (no dynamic regularisation fired)
+    assert mf.nreg == 0 and F.regularize_count == 0
+
+
+def test_amd_and_nd_are_permutations_and_reduce_fill(cb):
+    from oracle import qdldl as oq
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, small_instances(cb)["C3s"])
+    N = KKT.shape[0]
+    nat = oq.QDLDLFactorisation(KKT, Ds, perm=np.arange(N))
+    for perm in (oq.amd_order(KKT), oq.nd_order(KKT, 1.5, 32)):
+        assert sorted(perm.tolist()) == list(range(N))
+        F = oq.QDLDLFactorisation(KKT, Ds, perm=perm)
+        assert F.nnzL < nat.nnzL
