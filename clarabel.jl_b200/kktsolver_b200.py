@@ -111,6 +111,17 @@ class B200KKTSolver:
         self.KKT, self.map = assemble_kkt_matrix(P, A, cones)
         self.p = cones.p
         self.Dsigns = fill_Dsigns(m, n, self.p)
+        # Ordering choice.  Nested dissection gives the shallow, wide trees the level-scheduled
+        # kernels want, but its separators can cut through the dense clique of a PSD cone block;
+        # late in the IP iteration those blocks have a dynamic range > 1e10 and a split clique was
+        # observed to produce wrong-sign pivots (dynamic regularisation firing, growth, NaN) where
+        # the reference's AMD order does not.  Problems with dense PSD blocks therefore keep the
+        # reference's AMD-class ordering (their fronts are large: parallelism comes from inside
+        # the fronts, not from the tree).
+        if "ordering" not in cs_over:
+            from .cones import PSD
+            has_psd = bool(((cones.types == PSD) & (cones.dims > 2)).any())
+            cs_over = dict(cs_over, ordering=0 if has_psd else 1)
         self.ldl = B200DirectLDLSolver(self.KKT, self.Dsigns, settings, **cs_over)
         L, h = self.ldl._L, self.ldl._h
         mp = self.map
