@@ -125,6 +125,7 @@ struct cb200_handle {
     int64_t nsoc = 0, nsocrows = 0;
     DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
     double last_eps = 0;
+    bool resident = false;
     Timers tm;
 };
 
@@ -564,10 +565,12 @@ int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_e
         if (len <= 0) return cudaSuccess;
         return cudaMemcpyAsync(dst, src, len * sizeof(double), cudaMemcpyHostToDevice, st);
     };
-    CUDA_OK(h2d(h->d_w.p, w, h->m));
-    CUDA_OK(h2d(h->d_eta.p, soc_eta, h->nsoc)); CUDA_OK(h2d(h->d_socd.p, soc_d, h->nsoc));
-    CUDA_OK(h2d(h->d_socu.p, soc_u, h->nsocrows)); CUDA_OK(h2d(h->d_socv.p, soc_v, h->nsocrows));
-    CUDA_OK(h2d(h->d_psd_R.p, psd_R, h->psd_rtotal));
+    if (!h->resident) {
+        CUDA_OK(h2d(h->d_w.p, w, h->m));
+        CUDA_OK(h2d(h->d_eta.p, soc_eta, h->nsoc)); CUDA_OK(h2d(h->d_socd.p, soc_d, h->nsoc));
+        CUDA_OK(h2d(h->d_socu.p, soc_u, h->nsocrows)); CUDA_OK(h2d(h->d_socv.p, soc_v, h->nsocrows));
+        CUDA_OK(h2d(h->d_psd_R.p, psd_R, h->psd_rtotal));
+    }
     if (h->ndiag) {
         k_hs_diag<<<nblk(h->ndiag, 256), 256, 0, st>>>(h->ndiag, h->d_dg_kind.p, h->d_dg_midx.p, h->d_dg_cone.p,
                                                        h->d_dg_map.p, h->d_w.p, h->d_eta.p, h->d_socd.p, h->d_nz.p);
@@ -606,8 +609,10 @@ int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
     const int64_t N = h->N, n = h->n, m = h->m;
     if (ir_rounds) *ir_rounds = 0;
     if (N == 0) return 0;
-    if (n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!h->resident) {
+        if (n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     k_build_rhs<<<nblk(N, 256), 256, 0, st>>>(h->d_rx.p, h->d_rz.p, n, m, N, h->d_b.p);
     CUDA_OK(cudaMemsetAsync(h->d_scal.p + 1, 0, sizeof(unsigned long long), st));
     k_absmax<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(h->d_b.p, N, h->d_scal.p + 1);
@@ -650,7 +655,7 @@ int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
     }
     // keep handle buffers consistent with the pointer swaps (kktsolver_directldl.jl:445)
     if (x != h->d_x.p) std::swap(h->d_x.p, h->d_dx.p);
-    if (ok) {
+    if (ok && !h->resident) {
         if (lhsx && n) CUDA_OK(cudaMemcpyAsync(lhsx, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (lhsz && m) CUDA_OK(cudaMemcpyAsync(lhsz, h->d_x.p + n, m * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -701,6 +706,8 @@ int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len) {
     for (int i = 0; i < len && i < 7; ++i) out[i] = v[i];
     return 0;
 }
+void* cb200_get_stream(cb200_handle* h) { return (void*)h->stream; }
+int32_t cb200_set_resident(cb200_handle* h, int32_t resident) { h->resident = resident != 0; return 0; }
 int32_t cb200_reset_timers(cb200_handle* h) {
     for (double& x : h->tm.ms) x = 0;
     h->tm.nfactor = h->tm.nsolve = h->tm.nlaunch = 0;

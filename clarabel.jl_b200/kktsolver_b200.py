@@ -101,6 +101,12 @@ class B200DirectLDLSolver:
     def reset_timers(self):
         self._L.cb200_reset_timers(self._h)
 
+    def stream_ptr(self):
+        return self._L.cb200_get_stream(self._h)
+
+    def set_resident(self, flag):
+        self._L.cb200_set_resident(self._h, int(bool(flag)))
+
 
 class B200KKTSolver:
     """OUTER boundary: AbstractKKTSolver over the fused C-ABI entry points."""

@@ -20,6 +20,7 @@ EXPORTED = [
     "cb200_refactor", "cb200_solve", "cb200_info",
     "cb200_set_maps", "cb200_update_cones", "cb200_solve_ir", "cb200_update_P", "cb200_update_A",
     "cb200_download", "cb200_get_timers", "cb200_reset_timers", "cb200_last_error",
+    "cb200_get_stream", "cb200_set_resident",
 ]
 
 
@@ -75,6 +76,8 @@ def lib():
         L.cb200_get_timers.argtypes = [P, P, I32]; L.cb200_get_timers.restype = I32
         L.cb200_reset_timers.argtypes = [P]; L.cb200_reset_timers.restype = I32
         L.cb200_last_error.restype = C.c_char_p
+        L.cb200_get_stream.argtypes = [P]; L.cb200_get_stream.restype = C.c_void_p
+        L.cb200_set_resident.argtypes = [P, I32]; L.cb200_set_resident.restype = I32
         _LIB = L
     return _LIB
 

@@ -127,6 +127,13 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len);
  * 1 factor, 2 triangular solves, 3 spmv/residual ; counters: 4 #factor, 5 #solves, 6 #kernel launches */
 int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len);
 int32_t cb200_reset_timers(cb200_handle* h);
+/* The CUDA stream (cudaStream_t) all of this handle's work is enqueued on, so a caller can
+ * bracket calls with its own events. */
+void*   cb200_get_stream(cb200_handle* h);
+/* resident != 0: cb200_update_cones / cb200_solve_ir skip their host<->device copies and work
+ * on the cone state / right-hand side already in HBM from the previous call (device-resident
+ * timing of the same kernels; results stay on the device). */
+int32_t cb200_set_resident(cb200_handle* h, int32_t resident);
 const char* cb200_last_error(void);
 
 #ifdef __cplusplus
