@@ -44,9 +44,8 @@ template <class T> struct DevBuf {
 struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0; };
 
 constexpr int NSMALL = 6;
-static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 160};
-constexpr int NSOLVE = 4;
-static const int kSolveNf[NSOLVE] = {32, 256, 1024, 1 << 30};
+static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
+constexpr int NSOLVE = 3;      // 0: single-column leaves, 1: warp per supernode, 2: CTA per supernode
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -93,7 +92,8 @@ struct cb200_handle {
     DevBuf<int32_t> d_perm;
     // symbolic
     DevBuf<int32_t> d_sn_first, d_rows, d_rel, d_child_ptr, d_child_list, d_batches;
-    DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff;
+    DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff, d_front_ptr, d_asm_base;
+    DevBuf<int32_t> d_asm_colptr, d_asm_src, d_asm_child;
     // numeric
     DevBuf<double> d_L, d_U, d_W, d_D, d_Dinv, d_uvec;
     DevBuf<double> d_b, d_x, d_e, d_dx, d_y, d_rx, d_rz;
@@ -136,6 +136,8 @@ DevSym devsym(cb200_handle* h) {
     d.sn_first = h->d_sn_first.p; d.rows_ptr = h->d_rows_ptr.p; d.rows = h->d_rows.p; d.rel = h->d_rel.p;
     d.child_ptr = h->d_child_ptr.p; d.child_list = h->d_child_list.p;
     d.panel_off = h->d_panel_off.p; d.upd_off = h->d_upd_off.p; d.dsign = h->d_dsign_perm.p;
+    d.front_ptr = h->d_front_ptr.p; d.asm_base = h->d_asm_base.p; d.asm_colptr = h->d_asm_colptr.p;
+    d.asm_src = h->d_asm_src.p; d.asm_child = h->d_asm_child.p;
     return d;
 }
 
@@ -146,7 +148,8 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 template <int T>
 int launch_small(cb200_handle* h, const Batch& b, int nfcap, RegParams rp) {
     if (b.cnt == 0) return 0;
-    size_t sm = (size_t)b.maxnf * b.maxnf * sizeof(double);
+    const int sbuf = std::min(SB, b.maxns);
+    size_t sm = ((size_t)b.maxnf * b.maxnf + (size_t)sbuf * sbuf) * sizeof(double);
     (void)nfcap;
     k_factor_small<T><<<b.cnt, T, sm, h->stream>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
                                                    h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
@@ -154,17 +157,47 @@ int launch_small(cb200_handle* h, const Batch& b, int nfcap, RegParams rp) {
     return 0;
 }
 
-template <int T> void launch_fwd(cb200_handle* h, const Batch& b) {
-    if (b.cnt == 0) return;
-    k_fwd<T><<<b.cnt, T, (size_t)b.maxnf * sizeof(double), h->stream>>>(
-        devsym(h), h->d_batches.p + b.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
-    LAUNCH(h);
+void launch_fwd_level(cb200_handle* h, const LevelPlan& P) {
+    DevSym ds = devsym(h);
+    const Batch& b0 = P.solve[0];
+    if (b0.cnt) {
+        k_fwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
+                                                             h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+    }
+    const Batch& b1 = P.solve[1];
+    if (b1.cnt) {
+        k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
+            ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+    }
+    const Batch& b2 = P.solve[2];
+    if (b2.cnt) {
+        k_fwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
+            ds, h->d_batches.p + b2.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+    }
 }
-template <int T> void launch_bwd(cb200_handle* h, const Batch& b) {
-    if (b.cnt == 0) return;
-    k_bwd<T><<<b.cnt, T, (size_t)b.maxnf * sizeof(double), h->stream>>>(
-        devsym(h), h->d_batches.p + b.off, h->d_L.p, h->d_Dinv.p, h->d_y.p);
-    LAUNCH(h);
+void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
+    DevSym ds = devsym(h);
+    const Batch& b2 = P.solve[2];
+    if (b2.cnt) {
+        k_bwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
+            ds, h->d_batches.p + b2.off, h->d_L.p, h->d_Dinv.p, h->d_y.p);
+        LAUNCH(h);
+    }
+    const Batch& b1 = P.solve[1];
+    if (b1.cnt) {
+        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
+            ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
+        LAUNCH(h);
+    }
+    const Batch& b0 = P.solve[0];
+    if (b0.cnt) {
+        k_bwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
+                                                             h->d_Dinv.p, h->d_y.p);
+        LAUNCH(h);
+    }
 }
 
 // zero the update blocks of the large fronts of one level
@@ -221,6 +254,8 @@ int factor(cb200_handle* h, bool static_reg) {
                                                                              h->d_W.p, wo);
                 h->tm.nlaunch += 2;
             }
+            k_invert_diag_large<<<dim3(nblk(B.maxns, SB), B.cnt), 64, 2 * SB * SB * sizeof(double), st>>>(ds, bl, h->d_L.p);
+            LAUNCH(h);
         }
     }
     h->tm.end(st);
@@ -237,13 +272,11 @@ int tri_solve(cb200_handle* h, const double* d_rhs, double* d_sol) {
     if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
     for (int lv = 0; lv < S.nlevels; ++lv) {
         const LevelPlan& P = h->plan[lv];
-        launch_fwd<32>(h, P.solve[0]); launch_fwd<64>(h, P.solve[1]);
-        launch_fwd<128>(h, P.solve[2]); launch_fwd<256>(h, P.solve[3]);
+        launch_fwd_level(h, P);
     }
     for (int lv = S.nlevels - 1; lv >= 0; --lv) {
         const LevelPlan& P = h->plan[lv];
-        launch_bwd<32>(h, P.solve[0]); launch_bwd<64>(h, P.solve[1]);
-        launch_bwd<128>(h, P.solve[2]); launch_bwd<256>(h, P.solve[3]);
+        launch_bwd_level(h, P);
     }
     if (h->N) { k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h); }
     h->tm.end(st);
@@ -339,6 +372,9 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_rows.upload(S.rows, s)); CUDA_OK(h->d_rel.upload(S.rel, s));
         CUDA_OK(h->d_child_ptr.upload(S.child_ptr, s)); CUDA_OK(h->d_child_list.upload(S.child_list, s));
         CUDA_OK(h->d_panel_off.upload(S.panel_off, s)); CUDA_OK(h->d_upd_off.upload(S.upd_off, s));
+        CUDA_OK(h->d_front_ptr.upload(S.front_ptr, s)); CUDA_OK(h->d_asm_base.upload(S.asm_base, s));
+        CUDA_OK(h->d_asm_colptr.upload(S.asm_colptr, s)); CUDA_OK(h->d_asm_src.upload(S.asm_src, s));
+        CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
         // ---- level plans
         h->plan.assign(S.nlevels, LevelPlan());
         std::vector<int32_t> batches; std::vector<int64_t> woff;
@@ -362,7 +398,8 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                 int nf = S.ns(sn) + S.nr(sn);
                 int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
                 cls[c].push_back(sn);
-                int d = 0; while (nf > kSolveNf[d]) ++d;
+                const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
+                const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : 2);
                 scl[d].push_back(sn);
             }
             LevelPlan& P = h->plan[lv];
@@ -386,11 +423,15 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), s));
         // opt in to large dynamic shared memory for the bigger small-front classes
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     160 * 160 * (int)sizeof(double)));
+                                     (152 * 152 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     64 * 64 * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                     (64 * 64 + SB * SB) * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_factor_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (32 * 32 + SB * SB) * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_invert_diag_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     2 * SB * SB * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); delete h; return -4; }
         CUDA_OK(cudaStreamSynchronize(s));
         *out = h;

@@ -25,9 +25,43 @@ struct DevSym {                 // device copies of the Symbolic arrays
     const int64_t* panel_off;
     const int64_t* upd_off;
     const int8_t*  dsign;       // [N] permuted pivot signs
+    const int64_t* front_ptr;   // destination-owner assembly maps (symbolic.h)
+    const int64_t* asm_base;
+    const int32_t* asm_colptr;
+    const int32_t* asm_src;
+    const int32_t* asm_child;
 };
 
 struct RegParams { double eps, delta; int enable; };
+
+
+// ------------------------------------------------------------------ inverted diagonal blocks
+// The triangular solves never substitute column by column: every SBxSB diagonal block of the
+// unit-lower L11 of a supernode is replaced, in place, by its inverse at factorisation time, so
+// a solve is a sequence of block GEMVs  x_kb = inv(L_kb,kb) w_kb ;  w_rest -= L[rest,kb] x_kb
+// with no per-column dependency chain (chain length ns/SB instead of ns).
+constexpr int SB = 64;
+
+// Invert the unit-lower sb x sb block T (column-major, leading dimension ld) in place.
+// `buf` is scratch of SB*SB doubles in shared memory.  All threads of the CTA must call.
+__device__ __forceinline__ void invert_unit_lower_block(double* T, int ld, int sb, double* buf,
+                                                        int tid, int nthreads) {
+    for (int e = tid; e < sb * sb; e += nthreads) {
+        const int i = e % sb, j = e / sb;
+        buf[e] = (i > j) ? T[i + j * ld] : 0.0;
+    }
+    __syncthreads();
+    // column j of X = T^-1:  x_i = -sum_{k=j}^{i-1} T_ik x_k  (x_j = 1), one thread per column
+    for (int j = tid; j < sb; j += nthreads) {
+        double* X = T + j * ld;
+        for (int i = j + 1; i < sb; ++i) {
+            double acc = -buf[i + j * sb];                     // k = j term (x_j = 1)
+            for (int k = j + 1; k < i; ++k) acc -= buf[i + k * sb] * X[k];
+            X[i] = acc;
+        }
+    }
+    __syncthreads();
+}
 
 // ------------------------------------------------------------------ G4 small fronts
 // One CTA per front; the whole front lives in shared memory.  Fuses: extend-add of the children's
@@ -51,23 +85,23 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
     for (int i = tid; i < nf * ns; i += THREADS) F[i] = Lp[i];
     for (int i = nf * ns + tid; i < nf * nf; i += THREADS) F[i] = 0.0;
     __syncthreads();
-    // 2. extend-add children (sequential over children => deterministic sums)
-    for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
-        const int c = S.child_list[q];
-        const int64_t rp0 = S.rows_ptr[c];
-        const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
-        const int32_t* relc = S.rel + rp0;
-        const double* Uc = Ust + S.upd_off[c];
-        if (THREADS >= 64) {
-            const int lane = tid & 31, wid = tid >> 5;
-            for (int j = wid; j < nrc; j += THREADS / 32) {
-                const int dj = relc[j] * nf;
-                for (int i = j + lane; i < nrc; i += 32) F[relc[i] + dj] += Uc[i + (int64_t)j * nrc];
-            }
-        } else {
-            for (int e = tid; e < nrc * nrc; e += THREADS) {
-                const int i = e % nrc, j = e / nrc;
-                if (i >= j) F[relc[i] + relc[j] * nf] += Uc[e];
+    // 2. extend-add, destination-owner form: warp w owns front columns d = w, w+NW, ...; the
+    // sources of a column are ordered by child => deterministic sums, no barrier per child
+    {
+        const int lane_ = tid & 31, wid_ = tid >> 5;
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int d = wid_; d < nf; d += THREADS / 32) {
+            double* dst = F + d * nf;
+            for (int e = cp[d]; e < cp[d + 1]; ++e) {
+                const int q = S.asm_src[base + e];
+                const int c = S.asm_child[base + e];
+                const int64_t rp0 = S.rows_ptr[c];
+                const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
+                const int j = (int)(q - rp0);
+                const int32_t* relc = S.rel + rp0;
+                const double* src = Ust + S.upd_off[c] + (int64_t)j * nrc;
+                for (int i = j + lane_; i < nrc; i += 32) dst[relc[i]] += src[i];
             }
         }
         __syncthreads();
@@ -95,6 +129,14 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
         }
         __syncthreads();
     }
+    // 3b. replace the diagonal blocks of L11 by their inverses (see invert_unit_lower_block)
+    {
+        double* buf = F + nf * nf;
+        for (int kb = 0; kb < ns; kb += SB) {
+            const int sb = min(SB, ns - kb);
+            if (sb > 1) invert_unit_lower_block(F + kb + kb * nf, nf, sb, buf, tid, THREADS);
+        }
+    }
     // 4. write back
     for (int i = tid; i < nf * ns; i += THREADS) Lp[i] = F[i];
     if (nr > 0) {
@@ -107,9 +149,9 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
 }
 
 // ------------------------------------------------------------------ G6 assembly for large fronts
-// grid (chunks, nbatch).  Chunk c owns destination columns [c*CW, (c+1)*CW) of the parent front,
-// so different CTAs never write the same entry; children are processed in order.
-constexpr int ASM_CW = 32;
+// grid (ceil(maxnf / 8), nbatch), 256 threads: one warp per destination column of the front;
+// sources ordered by child (deterministic), no inter-warp conflicts, no barriers.
+constexpr int ASM_CW = 8;
 __global__ void __launch_bounds__(256)
 k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ Lst,
                  double* __restrict__ Ust) {
@@ -118,31 +160,23 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
     const int ns = S.sn_first[s + 1] - f;
     const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int nf = ns + nr;
-    const int c0 = blockIdx.x * ASM_CW, c1 = min(nf, c0 + ASM_CW);
-    if (c0 >= nf) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int d = blockIdx.x * ASM_CW + wid;
+    if (d >= nf) return;
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
-        const int c = S.child_list[q];
+    double* dst = d < ns ? Lp + (int64_t)d * nf : Us + (int64_t)(d - ns) * nr - ns;
+    const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+    const int64_t base = S.asm_base[s];
+    for (int e = cp[d]; e < cp[d + 1]; ++e) {
+        const int q = S.asm_src[base + e];
+        const int c = S.asm_child[base + e];
         const int64_t rp0 = S.rows_ptr[c];
         const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
+        const int j = (int)(q - rp0);
         const int32_t* relc = S.rel + rp0;
-        const double* Uc = Ust + S.upd_off[c];
-        // child columns whose destination falls into [c0, c1): rel is increasing -> binary search
-        int lo = 0, hi = nrc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < c0) lo = mid + 1; else hi = mid; }
-        const int jb = lo;
-        hi = nrc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < c1) lo = mid + 1; else hi = mid; }
-        const int je = lo;
-        for (int j = jb + wid; j < je; j += 8) {
-            const int dj = relc[j];
-            double* dst = dj < ns ? Lp + (int64_t)dj * nf : Us + (int64_t)(dj - ns) * nr - ns;
-            const double* src = Uc + (int64_t)j * nrc;
-            for (int i = j + lane; i < nrc; i += 32) dst[relc[i]] += src[i];
-        }
-        __syncthreads();   // (only orders this CTA's own adds; kept for clarity)
+        const double* src = Ust + S.upd_off[c] + (int64_t)j * nrc;
+        for (int i = j + lane; i < nrc; i += 32) dst[relc[i]] += src[i];
     }
 }
 
@@ -315,6 +349,28 @@ k_update_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __re
     }
 }
 
+
+// In-place inversion of the SBxSB diagonal blocks of L11 for the large fronts of a level.
+// grid (max blocks per front, nbatch), 64 threads.
+__global__ void __launch_bounds__(64)
+k_invert_diag_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ Lst) {
+    extern __shared__ double T[];          // 2 * SB * SB doubles (dynamic: above the 48 KB static cap)
+    double* buf = T + SB * SB;
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int kb = blockIdx.x * SB;
+    if (kb >= ns) return;
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int sb = min(SB, ns - kb);
+    double* Lp = Lst + S.panel_off[s] + (int64_t)kb * nf + kb;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < sb * sb; e += 64) { const int i = e % sb, j = e / sb; T[i + j * SB] = Lp[i + (int64_t)j * nf]; }
+    __syncthreads();
+    invert_unit_lower_block(T, SB, sb, buf, tid, 64);
+    for (int e = tid; e < sb * sb; e += 64) { const int i = e % sb, j = e / sb; if (i > j) Lp[i + (int64_t)j * nf] = T[i + j * SB]; }
+}
+
 // ------------------------------------------------------------------ scatter / regularisation
 __global__ void k_scatter(const double* __restrict__ nz, const int64_t* __restrict__ amap,
                           int64_t n, double* __restrict__ Lst) {
@@ -363,13 +419,125 @@ __global__ void k_unpack_perm(const double* __restrict__ y, const int32_t* __res
 }
 
 // Forward sweep, multifrontal form (deterministic, no atomics): per supernode
-//   w = [y_s ; 0] + sum_children extend(u_c);  w <- L^{-1} w (unit lower, all nf rows);
-//   y_s = w[0:ns] * (1: stored unscaled),  u_s = w[ns:]
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_fwd(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
-      double* __restrict__ y, double* __restrict__ uvec) {
+//   w = [y_s ; 0] + sum_children extend(u_c);
+//   for each SB block kb:  x = inv(L_kb,kb) w_kb ;  w[kb+sb:] -= L[kb+sb:, kb:kb+sb] x
+//   y_s = w[0:ns],  u_s = w[ns:]
+// Backward sweep:  w = [D^-1 y_s ; x[R_s]] ;  for kb descending:
+//   t = w_kb - L[kb+sb:, kb:kb+sb]' w[kb+sb:] ;  w_kb = inv(L_kb,kb)' t
+
+// --- leaves with a single pivot column and no children: one thread per supernode
+__global__ void __launch_bounds__(128)
+k_fwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
+           double* __restrict__ y, double* __restrict__ uvec) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const double* Lp = Lst + S.panel_off[s];
+    const double x = y[f];
+    for (int i = 0; i < nr; ++i) uvec[rp + i] = -Lp[1 + i] * x;
+}
+__global__ void __launch_bounds__(128)
+k_bwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
+           const double* __restrict__ Dinv, double* __restrict__ y) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const double* Lp = Lst + S.panel_off[s];
+    double acc = y[f] * Dinv[f];
+    for (int i = 0; i < nr; ++i) acc -= Lp[1 + i] * y[S.rows[rp + i]];
+    y[f] = acc;
+}
+
+// --- narrow supernodes (ns <= 32): one warp per supernode, WPB warps per CTA
+constexpr int WPB = 8;
+__global__ void __launch_bounds__(WPB * 32)
+k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
+           const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int idx = blockIdx.x * WPB + wid;
+    if (idx >= count) return;
+    double* w = smem + (size_t)wid * maxnf;
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const int nf = ns + nr;
+    {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int i = lane; i < nf; i += 32) {
+            double acc = i < ns ? y[f + i] : 0.0;
+            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+            w[i] = acc;
+        }
+    }
+    __syncwarp();
+    const double* Lp = Lst + S.panel_off[s];
+    double xi = 0.0;
+    if (lane < ns) {
+        xi = w[lane];
+        for (int j = 0; j < lane; ++j) xi += Lp[(int64_t)j * nf + lane] * w[j];
+    }
+    __syncwarp();
+    if (lane < ns) { w[lane] = xi; y[f + lane] = xi; }
+    __syncwarp();
+    for (int r = ns + lane; r < nf; r += 32) {
+        double acc = w[r];
+        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * nf + r] * w[j];
+        uvec[rp + r - ns] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(WPB * 32)
+k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
+           const double* __restrict__ Lst, const double* __restrict__ Dinv, double* __restrict__ y) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int idx = blockIdx.x * WPB + wid;
+    if (idx >= count) return;
+    double* w = smem + (size_t)wid * maxnf;
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const int nf = ns + nr;
+    for (int i = lane; i < nf; i += 32) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
+    __syncwarp();
+    const double* Lp = Lst + S.panel_off[s];
+    // t_j = w_j - sum_r L[r,j] w_r  (lane j keeps t_j)
+    double tj = 0.0;
+    for (int j = 0; j < ns; ++j) {
+        const double* cj = Lp + (int64_t)j * nf;
+        double acc = 0.0;
+        for (int r = ns + lane; r < nf; r += 32) acc += cj[r] * w[r];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == j) tj = w[j] - acc;
+    }
+    // x_j = t_j + sum_{i>j} Linv[i,j] t_i
+    double xj = tj;
+    for (int i = 1; i < ns; ++i) {
+        const double ti = __shfl_sync(0xffffffffu, tj, i);
+        if (lane < i && lane < ns) xj += Lp[(int64_t)lane * nf + i] * ti;
+    }
+    if (lane < ns) y[f + lane] = xj;
+}
+
+// --- wide supernodes: one CTA (256 threads) per supernode, blocked over SB pivot columns
+__global__ void __launch_bounds__(256)
+k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
+          double* __restrict__ y, double* __restrict__ uvec) {
     extern __shared__ double w[];
+    __shared__ double xs[SB];
+    __shared__ double part[4][SB];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -377,34 +545,57 @@ k_fwd(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Ls
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
     const int tid = threadIdx.x;
-    for (int i = tid; i < nf; i += THREADS) w[i] = i < ns ? y[f + i] : 0.0;
+    {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int i = tid; i < nf; i += 256) {
+            double acc = i < ns ? y[f + i] : 0.0;
+            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+            w[i] = acc;
+        }
+    }
     __syncthreads();
-    for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
-        const int c = S.child_list[q];
-        const int64_t rp0 = S.rows_ptr[c];
-        const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
-        for (int i = tid; i < nrc; i += THREADS) w[S.rel[rp0 + i]] += uvec[rp0 + i];
-        __syncthreads();
-    }
     const double* Lp = Lst + S.panel_off[s];
-    for (int k = 0; k < ns; ++k) {
-        const double yk = w[k];
-        const double* ck = Lp + (int64_t)k * nf;
-        for (int i = k + 1 + tid; i < nf; i += THREADS) w[i] -= ck[i] * yk;
+    for (int kb = 0; kb < ns; kb += SB) {
+        const int sb = min(SB, ns - kb);
+        // diagonal block: x_i = w_i + sum_{j<i} Linv[i,j] w_j ; 4 threads per row split j
+        {
+            const int i = tid & 63, qd = tid >> 6;
+            double acc = 0.0;
+            if (i < sb) {
+                const double* row = Lp + (int64_t)kb * nf + kb + i;
+                for (int j = qd; j < i; j += 4) acc += row[(int64_t)j * nf] * w[kb + j];
+            }
+            part[qd][i] = acc;
+        }
+        __syncthreads();
+        if (tid < sb) {
+            const double x = w[kb + tid] + part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+            xs[tid] = x;
+        }
+        __syncthreads();
+        if (tid < sb) w[kb + tid] = xs[tid];
+        // rows below the block
+        const double* blk = Lp + (int64_t)kb * nf;
+        for (int r = kb + sb + tid; r < nf; r += 256) {
+            double acc = w[r];
+            const double* rowp = blk + r;
+#pragma unroll 8
+            for (int j = 0; j < sb; ++j) acc -= rowp[(int64_t)j * nf] * xs[j];
+            w[r] = acc;
+        }
         __syncthreads();
     }
-    for (int i = tid; i < nf; i += THREADS) {
+    for (int i = tid; i < nf; i += 256) {
         if (i < ns) y[f + i] = w[i]; else uvec[rp + i - ns] = w[i];
     }
 }
 
-// Backward sweep: x_s = L11^{-T} (D^{-1} y_s - L21' x[R_s])
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_bwd(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
-      const double* __restrict__ Dinv, double* __restrict__ y) {
+__global__ void __launch_bounds__(256)
+k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
+          const double* __restrict__ Dinv, double* __restrict__ y) {
     extern __shared__ double w[];
-    __shared__ double red[32];
+    __shared__ double ts[SB];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -412,30 +603,33 @@ k_bwd(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Ls
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < nf; i += THREADS)
-        w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
+    for (int i = tid; i < nf; i += 256) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
     __syncthreads();
     const double* Lp = Lst + S.panel_off[s];
-    for (int k = ns - 1; k >= 0; --k) {
-        const double* ck = Lp + (int64_t)k * nf;
-        double acc = 0.0;
-        for (int i = k + 1 + tid; i < nf; i += THREADS) acc += ck[i] * w[i];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (THREADS > 32) {
-            if (lane == 0) red[wid] = acc;
-            __syncthreads();
-            if (tid == 0) {
-                double t = 0.0;
-                for (int q = 0; q < THREADS / 32; ++q) t += red[q];
-                w[k] -= t;
-            }
-            __syncthreads();
-        } else {
-            if (tid == 0) w[k] -= acc;
-            __syncwarp();
+    const int nblk = (ns + SB - 1) / SB;
+    for (int bi = nblk - 1; bi >= 0; --bi) {
+        const int kb = bi * SB;
+        const int sb = min(SB, ns - kb);
+        // t_j = w_j - sum_{r >= kb+sb} L[r, kb+j] w_r : one warp per column, 8 columns at a time
+        for (int j = wid; j < sb; j += 8) {
+            const double* cj = Lp + (int64_t)(kb + j) * nf;
+            double acc = 0.0;
+            for (int r = kb + sb + lane; r < nf; r += 32) acc += cj[r] * w[r];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) ts[j] = w[kb + j] - acc;
         }
+        __syncthreads();
+        // x_j = t_j + sum_{i>j} Linv[i,j] t_i : warp per column j (reads down column j)
+        for (int j = wid; j < sb; j += 8) {
+            const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
+            double acc = 0.0;
+            for (int i = j + 1 + lane; i < sb; i += 32) acc += cj[i] * ts[i];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) w[kb + j] = ts[j] + acc;
+        }
+        __syncthreads();
     }
-    for (int i = tid; i < ns; i += THREADS) y[f + i] = w[i];
+    for (int i = tid; i < ns; i += 256) y[f + i] = w[i];
 }
 
 // ------------------------------------------------------------------ G8 residual e = b - K x

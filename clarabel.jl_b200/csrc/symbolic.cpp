@@ -306,6 +306,38 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             }
         }
     }
+    // destination-owner assembly maps
+    {
+        S.front_ptr.assign(ns2 + 1, 0); S.asm_base.assign(ns2 + 1, 0);
+        for (int32_t s = 0; s < ns2; ++s) {
+            int64_t nf = (int64_t)S.ns(s) + S.nr(s);
+            S.front_ptr[s + 1] = S.front_ptr[s] + nf + 1;
+            int64_t cnt = 0;
+            for (int32_t q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) cnt += S.nr(S.child_list[q]);
+            S.asm_base[s + 1] = S.asm_base[s] + cnt;
+        }
+        if (S.asm_base[ns2] > 2000000000LL || (int64_t)S.rows.size() > 2000000000LL)
+            throw std::runtime_error("symbolic: assembly map exceeds int32 indexing");
+        S.asm_colptr.assign(S.front_ptr[ns2], 0);
+        S.asm_src.resize(S.asm_base[ns2]); S.asm_child.resize(S.asm_base[ns2]);
+        for (int32_t s = 0; s < ns2; ++s) {
+            int32_t* cp = S.asm_colptr.data() + S.front_ptr[s];
+            const int64_t nf = (int64_t)S.ns(s) + S.nr(s);
+            for (int32_t q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
+                int32_t c = S.child_list[q];
+                for (int64_t r = S.rows_ptr[c]; r < S.rows_ptr[c + 1]; ++r) cp[S.rel[r] + 1]++;
+            }
+            for (int64_t d = 0; d < nf; ++d) cp[d + 1] += cp[d];
+            std::vector<int32_t> pos(cp, cp + nf);
+            for (int32_t q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
+                int32_t c = S.child_list[q];
+                for (int64_t r = S.rows_ptr[c]; r < S.rows_ptr[c + 1]; ++r) {
+                    int64_t e = S.asm_base[s] + pos[S.rel[r]]++;
+                    S.asm_src[e] = (int32_t)r; S.asm_child[e] = c;
+                }
+            }
+        }
+    }
     // scatter map of the original K entries into the panels
     S.a_map.resize(nnzK);
     for (int32_t j = 0; j < N; ++j)

@@ -35,6 +35,17 @@ struct Symbolic {
     std::vector<int64_t> panel_off; // [nsuper+1] doubles; panel s is nf x ns column-major, ld = nf
     std::vector<int64_t> upd_off;   // [nsuper+1] doubles; update block s is nr x nr, ld = nr
     std::vector<int64_t> a_map;     // [nnzK] K nz (original order) -> offset in panel storage
+    // Destination-owner form of the extend-add: for front s and front-local index d (column of
+    // the front for the factorisation, row of the work vector for the solves) the sources are
+    // asm_src[asm_base[s] + asm_colptr[front_ptr[s] + d] ...) ; each source is a global index q
+    // into rows/rel (child c = asm_child[.], child-local index j = q - rows_ptr[c]).  Sources of
+    // one destination are ordered by child, so sums are deterministic without atomics and a
+    // front with thousands of children is assembled in parallel over destinations.
+    std::vector<int64_t> front_ptr; // [nsuper+1] prefix sum of (nf+1)
+    std::vector<int64_t> asm_base;  // [nsuper+1]
+    std::vector<int32_t> asm_colptr;// [front_ptr.back()]
+    std::vector<int32_t> asm_src;   // [rows_total minus roots]
+    std::vector<int32_t> asm_child; // same length
     std::vector<int32_t> sn_level;  // [nsuper]
     int32_t nlevels = 0;
     std::vector<int32_t> level_ptr; // [nlevels+1]
