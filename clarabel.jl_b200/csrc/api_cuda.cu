@@ -41,11 +41,11 @@ template <class T> struct DevBuf {
     ~DevBuf() { free(); }
 };
 
-struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0; };
+struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0; };
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
-constexpr int NSOLVE = 3;      // 0: single-column leaves, 1: warp per supernode, 2: CTA per supernode
+constexpr int NSOLVE = 4;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big)
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -75,6 +75,13 @@ struct Timers {
     ~Timers() { for (auto e : pool) cudaEventDestroy(e); }
 };
 
+struct GraphExec {
+    cudaGraphExec_t exec = nullptr;
+    double nlaunch = 0;
+    bool failed = false;
+    ~GraphExec() { if (exec) cudaGraphExecDestroy(exec); }
+};
+
 }  // namespace cb200
 
 using namespace cb200;
@@ -95,7 +102,7 @@ struct cb200_handle {
     DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff, d_front_ptr, d_asm_base;
     DevBuf<int32_t> d_asm_colptr, d_asm_src, d_asm_child;
     // numeric
-    DevBuf<double> d_L, d_U, d_W, d_D, d_Dinv, d_uvec;
+    DevBuf<double> d_L, d_U, d_W, d_D, d_Dinv, d_uvec, d_partial;
     DevBuf<double> d_b, d_x, d_e, d_dx, d_y, d_rx, d_rz;
     DevBuf<double> d_eps; DevBuf<unsigned long long> d_scal;   // [0] max|diag|, [1] normb, [2] norme
     DevBuf<unsigned int> d_nreg;
@@ -126,6 +133,7 @@ struct cb200_handle {
     DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
     double last_eps = 0;
     bool resident = false;
+    GraphExec g_factor[2], g_solve;     // CUDA graphs: factor (without/with static reg), solve sweeps
     Timers tm;
 };
 
@@ -177,9 +185,43 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P) {
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
     }
+    const Batch& b3 = P.solve[3];
+    if (b3.cnt) {
+        const int32_t* bl = h->d_batches.p + b3.off;
+        k_big_asm_fwd<<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+        const int npanel = nblk(b3.maxns, WP);
+        for (int pk = 0; pk < npanel; ++pk) {
+            k_big_tri_fwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, h->d_L.p, h->d_y.p);
+            const int rows_below = b3.maxnf - pk * WP;     // upper bound
+            if (rows_below > 0) {
+                k_big_gemv_fwd<<<dim3(nblk(rows_below, BRT), b3.cnt), BRT, 0, h->stream>>>(
+                    ds, bl, pk, h->d_L.p, h->d_y.p, h->d_uvec.p);
+                LAUNCH(h);
+            }
+            LAUNCH(h);
+        }
+    }
 }
 void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     DevSym ds = devsym(h);
+    const Batch& b3 = P.solve[3];
+    if (b3.cnt) {
+        const int32_t* bl = h->d_batches.p + b3.off;
+        const int npanel = nblk(b3.maxns, WP);
+        const int maxtiles = std::max(1, nblk(b3.maxnf, BRT));
+        for (int pk = npanel - 1; pk >= 0; --pk) {
+            const int rows_below = b3.maxnf - pk * WP;
+            if (rows_below > 0) {
+                k_big_gemvT_bwd<<<dim3(nblk(rows_below, BRT), b3.cnt), 256, 0, h->stream>>>(
+                    ds, bl, pk, maxtiles, h->d_L.p, h->d_y.p, h->d_partial.p);
+                LAUNCH(h);
+            }
+            k_big_tri_bwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, maxtiles, h->d_L.p, h->d_Dinv.p,
+                                                         h->d_partial.p, h->d_y.p);
+            LAUNCH(h);
+        }
+    }
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
         k_bwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
@@ -210,10 +252,37 @@ __global__ void k_zero_upd(DevSym S, const int32_t* batch, double* Ust) {
 }
 
 // numeric factorisation of whatever is in d_nz (+ optional on-device static regularisation)
-int factor(cb200_handle* h, bool static_reg) {
+// Replays `body` (a fixed sequence of stream operations on h->stream) through a CUDA graph: the
+// launch sequence of a factorisation / solve sweep only depends on the symbolic structure, so it
+// is captured once and relaunched with one call per IP iteration.
+template <class F> int run_captured(cb200_handle* h, GraphExec& g, F body) {
+    if (!h->st.use_cuda_graph || g.failed) return body();
+    if (!g.exec) {
+        const double l0 = h->tm.nlaunch;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError(); g.failed = true; return body();
+        }
+        int rc = body();
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        g.nlaunch = h->tm.nlaunch - l0; h->tm.nlaunch = l0;
+        if (rc != 0 || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError(); g.failed = true;
+            return rc != 0 ? rc : body();
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.failed = true; return body(); }
+    }
+    CUDA_OK(cudaGraphLaunch(g.exec, h->stream));
+    h->tm.nlaunch += g.nlaunch;
+    return 0;
+}
+
+int factor_body(cb200_handle* h, bool static_reg) {
     cudaStream_t st = h->stream;
     const auto& S = h->S;
-    h->tm.begin(Timers::FACTOR, st);
     CUDA_OK(cudaMemsetAsync(h->d_L.p, 0, h->d_L.n * sizeof(double), st));
     CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), st));
     if (h->nnzK) { k_scatter<<<nblk(h->nnzK, 256), 256, 0, st>>>(h->d_nz.p, h->d_amap.p, h->nnzK, h->d_L.p); LAUNCH(h); }
@@ -246,38 +315,54 @@ int factor(cb200_handle* h, bool static_reg) {
             k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
             h->tm.nlaunch += 2;
             for (int kb = 0; kb < B.maxns; kb += LNB) {
-                int rows_below = B.maxnf - kb;
-                k_panel_large<<<dim3(std::max(1, nblk(rows_below, LTR)), B.cnt), LTR, 0, st>>>(
+                const int rows_from = B.maxnf - kb;
+                if (kb > 0) {
+                    k_lpanel_update<<<dim3(nblk(rows_from, GBM), B.cnt), 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_D.p);
+                    LAUNCH(h);
+                }
+                k_panel_large<<<dim3(std::max(1, nblk(rows_from, LTR)), B.cnt), LTR, 0, st>>>(
                     ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
-                int T = nblk(rows_below, UT);
-                k_update_large<<<dim3(T * (T + 1) / 2, B.cnt), 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_U.p,
-                                                                             h->d_W.p, wo);
-                h->tm.nlaunch += 2;
+                LAUNCH(h);
             }
-            k_invert_diag_large<<<dim3(nblk(B.maxns, SB), B.cnt), 64, 2 * SB * SB * sizeof(double), st>>>(ds, bl, h->d_L.p);
+            {
+                const int T = nblk(B.maxnr, GBM);
+                if (T > 0) {
+                    k_schur_large<<<dim3(T * (T + 1) / 2, B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p, h->d_D.p);
+                    LAUNCH(h);
+                }
+            }
+            k_finish_large<<<dim3(nblk(B.maxns, SB), B.cnt), 64, 2 * SB * SB * sizeof(double), st>>>(
+                ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
     }
-    h->tm.end(st);
-    h->tm.nfactor += 1;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+int factor(cb200_handle* h, bool static_reg) {
+    h->tm.begin(Timers::FACTOR, h->stream);
+    int rc = run_captured(h, h->g_factor[static_reg ? 1 : 0], [&]() { return factor_body(h, static_reg); });
+    h->tm.end(h->stream);
+    h->tm.nfactor += 1;
+    return rc;
+}
+
 // y (permuted, in d_y) <- K^-1 : forward, diagonal, backward
+int sweeps_body(cb200_handle* h) {
+    const auto& S = h->S;
+    for (int lv = 0; lv < S.nlevels; ++lv) launch_fwd_level(h, h->plan[lv]);
+    for (int lv = S.nlevels - 1; lv >= 0; --lv) launch_bwd_level(h, h->plan[lv]);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int tri_solve(cb200_handle* h, const double* d_rhs, double* d_sol) {
     cudaStream_t st = h->stream;
-    const auto& S = h->S;
     h->tm.begin(Timers::SOLVE, st);
     if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
-    for (int lv = 0; lv < S.nlevels; ++lv) {
-        const LevelPlan& P = h->plan[lv];
-        launch_fwd_level(h, P);
-    }
-    for (int lv = S.nlevels - 1; lv >= 0; --lv) {
-        const LevelPlan& P = h->plan[lv];
-        launch_bwd_level(h, P);
-    }
+    int rc = run_captured(h, h->g_solve, [&]() { return sweeps_body(h); });
+    if (rc) return rc;
     if (h->N) { k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h); }
     h->tm.end(st);
     h->tm.nsolve += 1;
@@ -385,9 +470,10 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
             for (int32_t sn : v) {
                 int nf = S.ns(sn) + S.nr(sn);
                 b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
+                b.maxnr = std::max(b.maxnr, S.nr(sn));
                 batches.push_back(sn);
                 woff.push_back(large ? w : 0);
-                if (large) w += (int64_t)nf * LNB;
+                if (large) w += (int64_t)(S.ns(sn) + LNB) * LNB;   // parked diagonal blocks
             }
             if (large) { P.wtotal = w; wmax = std::max(wmax, w); }
         };
@@ -399,7 +485,8 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                 int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
                 cls[c].push_back(sn);
                 const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
-                const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : 2);
+                const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
+                const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2));
                 scl[d].push_back(sn);
             }
             LevelPlan& P = h->plan[lv];
@@ -414,6 +501,14 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
         CUDA_OK(h->d_D.alloc(N)); CUDA_OK(h->d_Dinv.alloc(N));
         CUDA_OK(h->d_uvec.alloc(std::max<size_t>(1, S.rows.size())));
+        {
+            size_t pmax = 1;
+            for (const LevelPlan& P : h->plan) {
+                const Batch& b3 = P.solve[3];
+                if (b3.cnt) pmax = std::max(pmax, (size_t)b3.cnt * std::max(1, nblk(b3.maxnf, BRT)) * WP);
+            }
+            CUDA_OK(h->d_partial.alloc(pmax));
+        }
         for (DevBuf<double>* b : {&h->d_b, &h->d_x, &h->d_e, &h->d_dx, &h->d_y}) {
             CUDA_OK(b->alloc(std::max<int64_t>(1, N)));
             CUDA_OK(cudaMemsetAsync(b->p, 0, std::max<int64_t>(1, N) * sizeof(double), s));
@@ -428,7 +523,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (64 * 64 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (32 * 32 + SB * SB) * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_invert_diag_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_OK(cudaFuncSetAttribute(k_finish_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      2 * SB * SB * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -181,16 +181,154 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
 }
 
 // ------------------------------------------------------------------ G5 large fronts, blocked
+// Left-looking blocked LDL' in global memory, batched over the large fronts of a level:
+//   for each pivot block J (LNB columns):
+//       k_lpanel_update : F[J.., J] -= L[J.., 0:J] * D[0:J] * L[J, 0:J]'      (GEMM, K = J)
+//       k_panel_large   : factor the LNB x LNB diagonal block, L[r, J] = F[r, J] L_JJ^-T D_J^-1
+//   k_schur_large       : F22 -= L21 * D * L21'   one GEMM with K = ns  (the Schur complement)
+//   k_finish_large      : move the parked diagonal blocks in, invert the SB x SB blocks of L11
+// The trailing matrix is read and written once (big-K GEMMs), not once per pivot block.
 constexpr int LNB = 32;        // pivot block width
 constexpr int LTR = 128;       // rows per CTA in the panel kernel
+constexpr int GBM = 64, GBK = 16;
 
 // Front-local element address: column g < ns lives in the panel, otherwise in the update block.
 __device__ __forceinline__ double* front_col(double* Lp, double* Us, int ns, int nr, int nf, int g) {
     return g < ns ? Lp + (int64_t)g * nf : Us + (int64_t)(g - ns) * nr - ns;
 }
 
+// acc (4 x BN/16 per thread) = sum_{k in [k0,k1)} L[rowA0 + i, k] * D[k] * L[rowB0 + j, k]
+// 256 threads, tile 64 x BN, K-step 16, register prefetch + double-buffered shared memory.
+template <int BN>
+__device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int nf,
+                                              const double* __restrict__ Dv, int rowA0, int rowB0,
+                                              int k0, int k1, double (&acc)[4][BN / 16],
+                                              double (*As)[GBK][GBM], double (*Bs)[GBK][BN]) {
+    constexpr int CN = BN / 16;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < CN; ++c) acc[a][c] = 0.0;
+    // loader mapping: element e = tid + 256 u ; row = e % 64, k = e / 64  (A: 4 per thread)
+    double ra[4], rb[BN / 16];
+    auto gload = [&](int kk) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u, r = e & 63, k = kk + (e >> 6);
+            const int gr = rowA0 + r;
+            ra[u] = (k < k1 && gr < nf) ? Lp[(int64_t)k * nf + gr] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < BN / 16; ++u) {
+            const int e = tid + 256 * u, r = e % BN, k = kk + e / BN;
+            const int gr = rowB0 + r;
+            rb[u] = (k < k1 && gr < nf) ? Lp[(int64_t)k * nf + gr] * Dv[k] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u; As[buf][e >> 6][e & 63] = ra[u]; }
+#pragma unroll
+        for (int u = 0; u < BN / 16; ++u) { const int e = tid + 256 * u; Bs[buf][e / BN][e % BN] = rb[u]; }
+    };
+    if (k0 >= k1) return;
+    gload(k0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kk = k0; kk < k1; kk += GBK) {
+        const bool more = kk + GBK < k1;
+        if (more) gload(kk + GBK);
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            double av[4], bv[CN];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[buf][k][tx * 4 + a];
+#pragma unroll
+            for (int c = 0; c < CN; ++c) bv[c] = Bs[buf][k][ty * CN + c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < CN; ++c) acc[a][c] += av[a] * bv[c];
+        }
+        if (more) { sstore(buf ^ 1); }
+        __syncthreads();
+        buf ^= 1;
+    }
+}
+
+// grid (row tiles of 64, nbatch): F[r, J0 + c] -= sum_{k < J0} L[r,k] D[k] L[J0+c, k], r >= J0
+__global__ void __launch_bounds__(256)
+k_lpanel_update(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict__ Lst,
+                const double* __restrict__ D) {
+    __shared__ double As[2][GBK][GBM];
+    __shared__ double Bs[2][GBK][LNB];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    if (J0 >= ns) return;
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int r0 = J0 + blockIdx.x * GBM;
+    if (r0 >= nf) return;
+    double* Lp = Lst + S.panel_off[s];
+    double acc[4][LNB / 16];
+    ldl_gemm_tile<LNB>(Lp, nf, D + f, r0, J0, 0, J0, acc, As, Bs);
+    const int nb = min(LNB, ns - J0);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int c = 0; c < LNB / 16; ++c) {
+        const int cj = ty * (LNB / 16) + c;
+        if (cj >= nb) continue;
+        double* col = Lp + (int64_t)(J0 + cj) * nf;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int gr = r0 + tx * 4 + a;
+            if (gr < nf && gr >= J0 + cj) col[gr] -= acc[a][c];
+        }
+    }
+}
+
+// grid (tile pairs ti >= tj over the nr x nr update block, nbatch): F22 -= L21 D L21'
+__global__ void __launch_bounds__(256)
+k_schur_large(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
+              double* __restrict__ Ust, const double* __restrict__ D) {
+    __shared__ double As[2][GBK][GBM];
+    __shared__ double Bs[2][GBK][GBM];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    const int T = (nr + GBM - 1) / GBM;
+    int idx = blockIdx.x;
+    if (idx >= T * (T + 1) / 2) return;
+    int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+    while (ti * (ti + 1) / 2 > idx) --ti;
+    const int tj = idx - ti * (ti + 1) / 2;
+    const double* Lp = Lst + S.panel_off[s];
+    double acc[4][4];
+    ldl_gemm_tile<GBM>(Lp, nf, D + f, ns + ti * GBM, ns + tj * GBM, 0, ns, acc, As, Bs);
+    double* Us = Ust + S.upd_off[s];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int gj = tj * GBM + ty * 4 + c;
+        if (gj >= nr) continue;
+        double* col = Us + (int64_t)gj * nr;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int gi = ti * GBM + tx * 4 + a;
+            if (gi < nr && gi >= gj) col[gi] -= acc[a][c];
+        }
+    }
+}
+
 // grid (row tiles, nbatch), 128 threads.  Every CTA factors the nb x nb diagonal block in shared
-// memory (redundantly: no inter-CTA dependency), then solves its rows against it.
+// memory (redundantly: no inter-CTA dependency), then solves its rows against it.  The factored
+// diagonal block is parked in `Wst` (siblings may still be reading the unfactored one).
 __global__ void __launch_bounds__(LTR)
 k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __restrict__ Lst,
               double* __restrict__ Wst, const int64_t* __restrict__ woff,
@@ -209,7 +347,6 @@ k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __res
     if (r0 >= nf && blockIdx.x != 0) return;
     double* Lp = Lst + S.panel_off[s];
     const int tid = threadIdx.x;
-    // load diagonal block (lower part)
     for (int e = tid; e < nb * nb; e += LTR) {
         const int i = e % nb, j = e / nb;
         A[i][j] = (i >= j) ? Lp[(int64_t)(kb + j) * nf + kb + i] : 0.0;
@@ -222,7 +359,6 @@ k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __res
         if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
         const double dinv = 1.0 / d;
         __syncthreads();
-        // trailing update inside the block: thread (i,j) pairs
         for (int e = tid; e < (nb - k - 1) * (nb - k - 1); e += LTR) {
             const int i = k + 1 + e % (nb - k - 1), j = k + 1 + e / (nb - k - 1);
             if (i >= j) A[i][j] -= A[i][k] * A[j][k] * dinv;
@@ -236,18 +372,13 @@ k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __res
         __syncthreads();
     }
     if (blockIdx.x == 0) {
-        // The factored diagonal block cannot be written in place here: sibling CTAs of this
-        // front may still be loading the unfactored block.  Park it in the (otherwise unused)
-        // rows [kb, kb+nb) of the W workspace; k_update_large copies it into the panel.
-        double* Wd = Wst + woff[blockIdx.y];
-        for (int e = tid; e < nb * nb; e += LTR) {
-            const int i = e % nb, j = e / nb;
-            if (i > j) Wd[(int64_t)j * nf + kb + i] = A[i][j];
-            else if (i == j) Wd[(int64_t)j * nf + kb + i] = dv[j];
+        double* Wd = Wst + woff[blockIdx.y] + (int64_t)(kb / LNB) * (LNB * LNB);
+        for (int e = tid; e < LNB * LNB; e += LTR) {
+            const int i = e % LNB, j = e / LNB;
+            Wd[e] = (i < nb && j < nb) ? (i > j ? A[i][j] : (i == j ? dv[j] : 0.0)) : 0.0;
         }
         for (int k = tid; k < nb; k += LTR) { D[f + kb + k] = dv[k]; Dinv[f + kb + k] = dinvs[k]; }
     }
-    // rows below the diagonal block: x * L11' = a ; L = x * D^-1 ; W = x
     const int r = r0 + tid;
     if (r < nf) {
         double x[LNB];
@@ -262,99 +393,18 @@ k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __res
                 x[j] = v;
             }
         }
-        double* W = Wst + woff[blockIdx.y];
 #pragma unroll
-        for (int j = 0; j < LNB; ++j) {
-            if (j < nb) {
-                Lp[(int64_t)(kb + j) * nf + r] = x[j] * dinvs[j];
-                W[(int64_t)j * nf + r] = x[j];
-            }
-        }
+        for (int j = 0; j < LNB; ++j) if (j < nb) Lp[(int64_t)(kb + j) * nf + r] = x[j] * dinvs[j];
     }
 }
 
-// grid (tile pairs, nbatch), 256 threads; 64x64 tile of the trailing matrix, K = nb (<= 32):
-// C[i][j] -= sum_k L[i][k] * W[j][k]   for i >= j (lower part), i, j in [kb+nb, nf).
-constexpr int UT = 64;
-__global__ void __launch_bounds__(256)
-k_update_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __restrict__ Lst,
-               double* __restrict__ Ust, const double* __restrict__ Wst,
-               const int64_t* __restrict__ woff) {
-    __shared__ double sL[LNB][UT + 1];
-    __shared__ double sW[LNB][UT + 1];
-    const int s = batch[blockIdx.y];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    if (kb >= ns) return;
-    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int nf = ns + nr;
-    const int nb = min(LNB, ns - kb);
-    const int t0 = kb + nb;
-    const int nt = nf - t0;
-    if (blockIdx.x == 0) {      // move the factored diagonal block from W into the panel
-        const double* Wd = Wst + woff[blockIdx.y];
-        double* Lpd = Lst + S.panel_off[s];
-        for (int e = threadIdx.x; e < nb * nb; e += 256) {
-            const int i = e % nb, j = e / nb;
-            if (i >= j) Lpd[(int64_t)(kb + j) * nf + kb + i] = Wd[(int64_t)j * nf + kb + i];
-        }
-    }
-    if (nt <= 0) return;
-    // linear tile index -> (ti >= tj)
-    const int T = (nt + UT - 1) / UT;
-    int idx = blockIdx.x;
-    if (idx >= T * (T + 1) / 2) return;
-    int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
-    while (ti * (ti + 1) / 2 > idx) --ti;
-    const int tj = idx - ti * (ti + 1) / 2;
-    const int i0 = t0 + ti * UT, j0 = t0 + tj * UT;
-    double* Lp = Lst + S.panel_off[s];
-    double* Us = Ust + S.upd_off[s];
-    const double* W = Wst + woff[blockIdx.y];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < UT * LNB; e += 256) {
-        const int r = e % UT, k = e / UT;
-        const int gi = i0 + r, gj = j0 + r;
-        sL[k][r] = (k < nb && gi < nf) ? Lp[(int64_t)(kb + k) * nf + gi] : 0.0;
-        sW[k][r] = (k < nb && gj < nf) ? W[(int64_t)k * nf + gj] : 0.0;
-    }
-    __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;     // 16 x 16 threads, 4 x 4 micro-tile each
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < LNB; ++k) {
-        double l[4], w[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { l[a] = sL[k][tx + 16 * a]; w[a] = sW[k][ty + 16 * a]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] += l[a] * w[b];
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int gj = j0 + ty + 16 * b;
-        if (gj >= nf) continue;
-        double* col = front_col(Lp, Us, ns, nr, nf, gj);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int gi = i0 + tx + 16 * a;
-            if (gi < nf && gi >= gj) col[gi] -= acc[a][b];
-        }
-    }
-}
-
-
-// In-place inversion of the SBxSB diagonal blocks of L11 for the large fronts of a level.
-// grid (max blocks per front, nbatch), 64 threads.
+// Finish the large fronts of a level: bring the parked (factored) LNB x LNB diagonal blocks into
+// the panel and replace every SB x SB diagonal block of L11 by its inverse.
+// grid (max SB-blocks per front, nbatch), 64 threads, dynamic smem 2*SB*SB doubles.
 __global__ void __launch_bounds__(64)
-k_invert_diag_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ Lst) {
-    extern __shared__ double T[];          // 2 * SB * SB doubles (dynamic: above the 48 KB static cap)
+k_finish_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ Lst,
+               const double* __restrict__ Wst, const int64_t* __restrict__ woff) {
+    extern __shared__ double T[];
     double* buf = T + SB * SB;
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
@@ -364,11 +414,28 @@ k_invert_diag_large(DevSym S, const int32_t* __restrict__ batch, double* __restr
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int sb = min(SB, ns - kb);
     double* Lp = Lst + S.panel_off[s] + (int64_t)kb * nf + kb;
+    const double* Wd = Wst + woff[blockIdx.y];
     const int tid = threadIdx.x;
-    for (int e = tid; e < sb * sb; e += 64) { const int i = e % sb, j = e / sb; T[i + j * SB] = Lp[i + (int64_t)j * nf]; }
+    for (int e = tid; e < sb * sb; e += 64) {
+        const int i = e % sb, j = e / sb;
+        const int bi = i / LNB, bj = j / LNB;
+        double v;
+        if (bi == bj) v = Wd[(int64_t)((kb / LNB) + bi) * (LNB * LNB) + (i % LNB) + (j % LNB) * LNB];
+        else v = Lp[i + (int64_t)j * nf];
+        T[i + j * SB] = v;
+    }
+    __syncthreads();
+    // keep the pivots (diagonal of the parked blocks) aside: the panel diagonal holds D
+    for (int i = tid; i < sb; i += 64) buf[i] = T[i + i * SB];
+    __syncthreads();
+    double dsave = (tid < sb) ? buf[tid] : 0.0;
     __syncthreads();
     invert_unit_lower_block(T, SB, sb, buf, tid, 64);
-    for (int e = tid; e < sb * sb; e += 64) { const int i = e % sb, j = e / sb; if (i > j) Lp[i + (int64_t)j * nf] = T[i + j * SB]; }
+    for (int e = tid; e < sb * sb; e += 64) {
+        const int i = e % sb, j = e / sb;
+        if (i > j) Lp[i + (int64_t)j * nf] = T[i + j * SB];
+    }
+    if (tid < sb) Lp[tid + (int64_t)tid * nf] = dsave;
 }
 
 // ------------------------------------------------------------------ scatter / regularisation
@@ -424,6 +491,68 @@ __global__ void k_unpack_perm(const double* __restrict__ y, const int32_t* __res
 //   y_s = w[0:ns],  u_s = w[ns:]
 // Backward sweep:  w = [D^-1 y_s ; x[R_s]] ;  for kb descending:
 //   t = w_kb - L[kb+sb:, kb:kb+sb]' w[kb+sb:] ;  w_kb = inv(L_kb,kb)' t
+
+
+// ---- latency-tolerant building blocks: all global loads of a step are issued as one batch of
+// independent loads (every L entry is used exactly once per solve, so the only thing that
+// matters is memory-level parallelism).
+
+// acc = sum_{j=q,q+4,...<i} row[j*ld] * w[j]   (j < SB), 16 loads in flight
+__device__ __forceinline__ double diag_row_dot(const double* __restrict__ row, int64_t ld, int i, int q,
+                                               const double* __restrict__ w) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int j = q + 4 * u; v[u] = (j < i) ? row[(int64_t)j * ld] : 0.0; }
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int j = q + 4 * u; if (j < i) acc += v[u] * w[j]; }
+    return acc;
+}
+
+// acc = sum_{j<sb} rowp[j*ld] * x[j]   (sb <= 64), two batches of 32 loads
+__device__ __forceinline__ double row_dot64(const double* __restrict__ rowp, int64_t ld, int sb,
+                                            const double* __restrict__ x) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int jb = 0; jb < 64; jb += 32) {
+        if (jb < sb) {
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = (jb + u < sb) ? rowp[(int64_t)(jb + u) * ld] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 32; u += 2) { a0 += v[u] * x[jb + u]; a1 += v[u + 1] * x[jb + u + 1]; }
+        }
+    }
+    return a0 + a1;
+}
+
+// Transposed products for 8 consecutive columns at once: out[u] = sum_{r=r0+lane,+32,..<r1} col_u[r]*w[r]
+// (warp-level; result valid on all lanes after the shuffles)
+__device__ __forceinline__ void cols8_dot(const double* __restrict__ base, int64_t ld, int ncol,
+                                          int r0, int r1, const double* __restrict__ w, int lane,
+                                          double out[8]) {
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = 0.0;
+    for (int r = r0 + lane; r < r1; r += 64) {
+        double v0[8], v1[8];
+        const bool two = (r + 32) < r1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0[u] = (u < ncol) ? base[(int64_t)u * ld + r] : 0.0;
+            v1[u] = (u < ncol && two) ? base[(int64_t)u * ld + r + 32] : 0.0;
+        }
+        const double w0 = w[r], w1 = two ? w[r + 32] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += v0[u] * w0 + v1[u] * w1;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        double v = a[u];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        out[u] = v;
+    }
+}
 
 // --- leaves with a single pivot column and no children: one thread per supernode
 __global__ void __launch_bounds__(128)
@@ -562,10 +691,7 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         {
             const int i = tid & 63, qd = tid >> 6;
             double acc = 0.0;
-            if (i < sb) {
-                const double* row = Lp + (int64_t)kb * nf + kb + i;
-                for (int j = qd; j < i; j += 4) acc += row[(int64_t)j * nf] * w[kb + j];
-            }
+            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * nf + kb + i, nf, i, qd, w + kb);
             part[qd][i] = acc;
         }
         __syncthreads();
@@ -577,13 +703,7 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         if (tid < sb) w[kb + tid] = xs[tid];
         // rows below the block
         const double* blk = Lp + (int64_t)kb * nf;
-        for (int r = kb + sb + tid; r < nf; r += 256) {
-            double acc = w[r];
-            const double* rowp = blk + r;
-#pragma unroll 8
-            for (int j = 0; j < sb; ++j) acc -= rowp[(int64_t)j * nf] * xs[j];
-            w[r] = acc;
-        }
+        for (int r = kb + sb + tid; r < nf; r += 256) w[r] -= row_dot64(blk + r, nf, sb, xs);
         __syncthreads();
     }
     for (int i = tid; i < nf; i += 256) {
@@ -611,25 +731,249 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         const int kb = bi * SB;
         const int sb = min(SB, ns - kb);
         // t_j = w_j - sum_{r >= kb+sb} L[r, kb+j] w_r : one warp per column, 8 columns at a time
-        for (int j = wid; j < sb; j += 8) {
-            const double* cj = Lp + (int64_t)(kb + j) * nf;
-            double acc = 0.0;
-            for (int r = kb + sb + lane; r < nf; r += 32) acc += cj[r] * w[r];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) ts[j] = w[kb + j] - acc;
+        {   // warp `wid` owns columns 8*wid .. 8*wid+7 of the block
+            const int j0 = wid * 8;
+            if (j0 < sb) {
+                double o8[8];
+                cols8_dot(Lp + (int64_t)(kb + j0) * nf, nf, min(8, sb - j0), kb + sb, nf, w, lane, o8);
+                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kb + j0 + lane] - o8[lane];
+            }
         }
         __syncthreads();
-        // x_j = t_j + sum_{i>j} Linv[i,j] t_i : warp per column j (reads down column j)
-        for (int j = wid; j < sb; j += 8) {
-            const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
-            double acc = 0.0;
-            for (int i = j + 1 + lane; i < sb; i += 32) acc += cj[i] * ts[i];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) w[kb + j] = ts[j] + acc;
+        {   // x_j = t_j + sum_{i>j} Linv[i,j] t_i
+            const int j0 = wid * 8;
+            if (j0 < sb) {
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    double v0 = 0.0, v1 = 0.0;
+                    if (j < sb) {
+                        const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
+                        const int i0 = lane, i1 = lane + 32;
+                        if (i0 > j && i0 < sb) v0 = cj[i0] * ts[i0];
+                        if (i1 > j && i1 < sb) v1 = cj[i1] * ts[i1];
+                    }
+                    a[u] = v0 + v1;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    double v = a[u];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == u && j0 + u < sb) w[kb + j0 + u] = ts[j0 + u] + v;
+                }
+            }
         }
         __syncthreads();
     }
     for (int i = tid; i < ns; i += 256) y[f + i] = w[i];
+}
+
+// --- big supernodes: several CTAs per supernode.  The pivot columns are processed in panels of
+// WP columns; per panel a 1-CTA triangle kernel (inverted 64-blocks inside) and a many-CTA GEMV
+// over all rows below the panel.  The work vector lives in place: top part in y[f..f+ns), bottom
+// part in uvec[rows_ptr[s]..).  Panels run as separate launches (stream order = dependency).
+constexpr int WP = 256;        // panel width
+constexpr int BRT = 256;       // rows per CTA in the GEMV kernels
+
+// w = [y_s ; 0] + sum of children contributions (destination-owner form); grid (row tiles, cnt)
+__global__ void __launch_bounds__(256)
+k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ y,
+              double* __restrict__ uvec) {
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nf) return;
+    const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+    const int64_t base = S.asm_base[s];
+    double acc = i < ns ? y[f + i] : 0.0;
+    for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+    if (i < ns) y[f + i] = acc; else uvec[rp + i - ns] = acc;
+}
+
+// forward triangle of panel pk: x = inv-blocked solve of L11[kb:kb+wp, kb:kb+wp]; grid (cnt)
+__global__ void __launch_bounds__(256)
+k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double* __restrict__ Lst,
+              double* __restrict__ y) {
+    __shared__ double w[WP];
+    __shared__ double xs[SB];
+    __shared__ double part[4][SB];
+    const int s = batch[blockIdx.x];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int kb0 = pk * WP;
+    if (kb0 >= ns) return;
+    const int wp = min(WP, ns - kb0);
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int tid = threadIdx.x;
+    if (tid < wp) w[tid] = y[f + kb0 + tid];
+    __syncthreads();
+    const double* Lp = Lst + S.panel_off[s];
+    for (int kk = 0; kk < wp; kk += SB) {
+        const int kb = kb0 + kk;
+        const int sb = min(SB, wp - kk);
+        {
+            const int i = tid & 63, qd = tid >> 6;
+            double acc = 0.0;
+            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * nf + kb + i, nf, i, qd, w + kk);
+            part[qd][i] = acc;
+        }
+        __syncthreads();
+        if (tid < sb) xs[tid] = w[kk + tid] + part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+        __syncthreads();
+        if (tid < sb) w[kk + tid] = xs[tid];
+        const double* blk = Lp + (int64_t)kb * nf + kb0;       // rows relative to panel start
+        for (int r = kk + sb + tid; r < wp; r += 256) w[r] -= row_dot64(blk + r, nf, sb, xs);
+        __syncthreads();
+    }
+    if (tid < wp) y[f + kb0 + tid] = w[tid];
+}
+
+// forward GEMV below panel pk: w[r] -= sum_j L[r, kb0+j] x_j ; grid (row tiles, cnt)
+__global__ void __launch_bounds__(BRT)
+k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double* __restrict__ Lst,
+               double* __restrict__ y, double* __restrict__ uvec) {
+    __shared__ double xs[WP];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int kb0 = pk * WP;
+    if (kb0 >= ns) return;
+    const int wp = min(WP, ns - kb0);
+    const int64_t rp = S.rows_ptr[s];
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
+    const int r0 = kb0 + wp + blockIdx.x * BRT;
+    if (r0 >= nf) return;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < wp; j += BRT) xs[j] = y[f + kb0 + j];
+    __syncthreads();
+    const int r = r0 + tid;
+    if (r >= nf) return;
+    const double* rowp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 16 <= wp; j += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * nf];
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+            a0 += v[u] * xs[j + u]; a1 += v[u + 1] * xs[j + u + 1];
+            a2 += v[u + 2] * xs[j + u + 2]; a3 += v[u + 3] * xs[j + u + 3];
+        }
+    }
+    for (; j < wp; ++j) a0 += rowp[(int64_t)j * nf] * xs[j];
+    const double acc = (a0 + a1) + (a2 + a3);
+    if (r < ns) y[f + r] -= acc; else uvec[rp + r - ns] -= acc;
+}
+
+// backward, transposed GEMV below panel pk: partial[tile][j] = sum_{r in tile} L[r, kb0+j] w_r
+// with w_r = y[f+r] (r < ns, already solved) or y[rows[r-ns]]; grid (row tiles, cnt)
+__global__ void __launch_bounds__(256)
+k_big_gemvT_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
+                const double* __restrict__ Lst, const double* __restrict__ y,
+                double* __restrict__ partial) {
+    __shared__ double ws[BRT];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int kb0 = pk * WP;
+    if (kb0 >= ns) return;
+    const int wp = min(WP, ns - kb0);
+    const int64_t rp = S.rows_ptr[s];
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
+    const int r0 = kb0 + wp + blockIdx.x * BRT;
+    if (r0 >= nf) return;
+    const int nrow = min(BRT, nf - r0);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < nrow) { const int r = r0 + tid; ws[tid] = r < ns ? y[f + r] : y[S.rows[rp + r - ns]]; }
+    __syncthreads();
+    double* out = partial + ((int64_t)blockIdx.y * maxtiles + blockIdx.x) * WP;
+    const double* Lp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r0;
+    for (int j = wid * 4; j < wp; j += 32) {          // 8 warps x 4 columns per pass
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = lane; i < nrow; i += 32) {
+            const double wv = ws[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (j + u < wp) a[u] += Lp[(int64_t)(j + u) * nf + i] * wv;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double v = a[u];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && j + u < wp) out[j + u] = v;
+        }
+    }
+}
+
+// backward triangle of panel pk: t = D^-1 y_panel - sum_tiles partial ; x = L11_panel^-T t ; grid (cnt)
+__global__ void __launch_bounds__(256)
+k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
+              const double* __restrict__ Lst, const double* __restrict__ Dinv,
+              const double* __restrict__ partial, double* __restrict__ y) {
+    __shared__ double w[WP];
+    __shared__ double ts[SB];
+    const int s = batch[blockIdx.x];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int kb0 = pk * WP;
+    if (kb0 >= ns) return;
+    const int wp = min(WP, ns - kb0);
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ntiles = (nf - kb0 - wp + BRT - 1) / BRT;
+    if (tid < wp) {
+        double acc = y[f + kb0 + tid] * Dinv[f + kb0 + tid];
+        const double* pp = partial + (int64_t)blockIdx.x * maxtiles * WP + tid;
+        for (int t = 0; t < ntiles; ++t) acc -= pp[(int64_t)t * WP];
+        w[tid] = acc;
+    }
+    __syncthreads();
+    const double* Lp = Lst + S.panel_off[s];
+    const int nsub = (wp + SB - 1) / SB;
+    for (int bi = nsub - 1; bi >= 0; --bi) {
+        const int kk = bi * SB;
+        const int kb = kb0 + kk;
+        const int sb = min(SB, wp - kk);
+        {
+            const int j0 = wid * 8;
+            if (j0 < sb) {
+                double o8[8];
+                cols8_dot(Lp + (int64_t)(kb + j0) * nf + kb0, nf, min(8, sb - j0), kk + sb, wp, w, lane, o8);
+                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kk + j0 + lane] - o8[lane];
+            }
+        }
+        __syncthreads();
+        {
+            const int j0 = wid * 8;
+            if (j0 < sb) {
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    double v0 = 0.0, v1 = 0.0;
+                    if (j < sb) {
+                        const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
+                        const int i0 = lane, i1 = lane + 32;
+                        if (i0 > j && i0 < sb) v0 = cj[i0] * ts[i0];
+                        if (i1 > j && i1 < sb) v1 = cj[i1] * ts[i1];
+                    }
+                    a[u] = v0 + v1;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    double v = a[u];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == u && j0 + u < sb) w[kk + j0 + u] = ts[j0 + u] + v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < wp) y[f + kb0 + tid] = w[tid];
 }
 
 // ------------------------------------------------------------------ G8 residual e = b - K x
