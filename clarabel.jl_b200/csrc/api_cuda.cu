@@ -314,15 +314,17 @@ int factor_body(cb200_handle* h, bool static_reg) {
             k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)maxnr * maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
             k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
             h->tm.nlaunch += 2;
-            for (int kb = 0; kb < B.maxns; kb += LNB) {
-                const int rows_from = B.maxnf - kb;
-                if (kb > 0) {
-                    k_lpanel_update<<<dim3(nblk(rows_from, GBM), B.cnt), 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_D.p);
+            const size_t sm64 = (size_t)(4 * GBK * GBM + 2 * PB * (PB + 1)) * sizeof(double);
+            for (int kb = 0; kb < B.maxns; kb += PB) {
+                k_diag64<<<B.cnt, 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
+                                                   rp, h->d_nreg.p);
+                LAUNCH(h);
+                const int rows_below = B.maxnf - kb - 1;
+                if (rows_below > 0) {
+                    k_rows64<<<dim3(nblk(rows_below, GBM), B.cnt), 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p,
+                                                                                     wo, h->d_D.p, h->d_Dinv.p);
                     LAUNCH(h);
                 }
-                k_panel_large<<<dim3(std::max(1, nblk(rows_from, LTR)), B.cnt), LTR, 0, st>>>(
-                    ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
-                LAUNCH(h);
             }
             {
                 const int T = nblk(B.maxnr, GBM);
@@ -331,7 +333,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                     LAUNCH(h);
                 }
             }
-            k_finish_large<<<dim3(nblk(B.maxns, SB), B.cnt), 64, 2 * SB * SB * sizeof(double), st>>>(
+            k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(
                 ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
@@ -473,7 +475,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                 b.maxnr = std::max(b.maxnr, S.nr(sn));
                 batches.push_back(sn);
                 woff.push_back(large ? w : 0);
-                if (large) w += (int64_t)(S.ns(sn) + LNB) * LNB;   // parked diagonal blocks
+                if (large) w += (int64_t)nblk(S.ns(sn), PB) * PB * PB;   // parked diagonal blocks
             }
             if (large) { P.wtotal = w; wmax = std::max(wmax, w); }
         };
@@ -523,8 +525,10 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (64 * 64 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (32 * 32 + SB * SB) * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_finish_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     2 * SB * SB * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_diag64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (4 * GBK * GBM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_rows64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (4 * GBK * GBM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); delete h; return -4; }

@@ -182,14 +182,11 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
 
 // ------------------------------------------------------------------ G5 large fronts, blocked
 // Left-looking blocked LDL' in global memory, batched over the large fronts of a level:
-//   for each pivot block J (LNB columns):
-//       k_lpanel_update : F[J.., J] -= L[J.., 0:J] * D[0:J] * L[J, 0:J]'      (GEMM, K = J)
-//       k_panel_large   : factor the LNB x LNB diagonal block, L[r, J] = F[r, J] L_JJ^-T D_J^-1
+//   for each pivot block J (64 columns): k_diag64 (GEMM update + LDL' + inverse of the diagonal
+//       block) and k_rows64 (GEMM update of the rows below, then multiply by inv(L_JJ)' D_J^-1)
 //   k_schur_large       : F22 -= L21 * D * L21'   one GEMM with K = ns  (the Schur complement)
-//   k_finish_large      : move the parked diagonal blocks in, invert the SB x SB blocks of L11
+//   k_finish_large      : move the parked inverted diagonal blocks into the panel
 // The trailing matrix is read and written once (big-K GEMMs), not once per pivot block.
-constexpr int LNB = 32;        // pivot block width
-constexpr int LTR = 128;       // rows per CTA in the panel kernel
 constexpr int GBM = 64, GBK = 16;
 
 // Front-local element address: column g < ns lives in the panel, otherwise in the update block.
@@ -259,33 +256,169 @@ __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int
     }
 }
 
-// grid (row tiles of 64, nbatch): F[r, J0 + c] -= sum_{k < J0} L[r,k] D[k] L[J0+c, k], r >= J0
+// Pivot block J (PB = 64 columns) of the large fronts of a level, two launches:
+//   k_diag64 : one CTA per front.  Dblk = F[J,J] - L[J,0:J] D L[J,0:J]' (GEMM), LDL' of the 64x64
+//              block by one warp (sign-based dynamic regularisation), inverse of its unit-lower
+//              factor.  Parks [inv(L_JJ) strictly lower ; d on the diagonal] in the workspace.
+//   k_rows64 : CTA per 64-row tile below the block.  T = F[rows,J] - L[rows,0:J] D L[J,0:J]'
+//              (GEMM, K = J), then L[rows,J] = T * inv(L_JJ)' * D_J^-1 (64x64x64 from smem).
+constexpr int PB = 64;
+
 __global__ void __launch_bounds__(256)
-k_lpanel_update(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict__ Lst,
-                const double* __restrict__ D) {
-    __shared__ double As[2][GBK][GBM];
-    __shared__ double Bs[2][GBK][LNB];
+k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __restrict__ Lst,
+         double* __restrict__ Wst, const int64_t* __restrict__ woff, double* __restrict__ D,
+         double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
+    extern __shared__ double smem[];
+    double (*As)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem);
+    double (*Bs)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem + 2 * GBK * GBM);
+    double* A = smem + 4 * GBK * GBM;                 // 64 x 65
+    const int s = batch[blockIdx.x];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    if (J0 >= ns) return;
+    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nb = min(PB, ns - J0);
+    const double* Lp = Lst + S.panel_off[s];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+    ldl_gemm_tile<GBM>(Lp, nf, D + f, J0, J0, 0, J0, acc, As, Bs);
+    if (J0 == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = tx * 4 + a, j = ty * 4 + c;
+            double v = 0.0;
+            if (i < nb && j < nb && i >= j) v = Lp[(int64_t)(J0 + j) * nf + J0 + i] - acc[a][c];
+            A[i + j * (PB + 1)] = v;                    // column-major, ld = 65
+        }
+    __syncthreads();
+    // right-looking LDL' of the block, all 8 warps (warp per trailing column)
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int k = 0; k < nb; ++k) {
+        double d = A[k + k * (PB + 1)];
+        const double sg = (double)S.dsign[f + J0 + k];
+        bool reg = false;
+        if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
+        const double dinv = 1.0 / d;
+        const double* ck = A + k * (PB + 1);
+        for (int j = k + 1 + wid; j < nb; j += 8) {
+            const double wj = ck[j] * dinv;
+            double* cj = A + j * (PB + 1);
+            for (int i = j + lane; i < nb; i += 32) cj[i] -= ck[i] * wj;
+        }
+        __syncthreads();
+        for (int i = k + 1 + tid; i < nb; i += 256) A[i + k * (PB + 1)] *= dinv;
+        if (tid == 0) {
+            A[k + k * (PB + 1)] = d; D[f + J0 + k] = d; Dinv[f + J0 + k] = dinv;
+            if (reg) atomicAdd(nreg, 1u);
+        }
+        __syncthreads();
+    }
+    // inverse of the unit-lower factor, 4 threads per column j: x_i = -(L_ij + sum_{j<k<i} L_ik x_k);
+    // the k-sum is split over the 4 threads of the group and reduced with shuffles.  X is written
+    // into the upper triangle of A (X[i][j] stored at A[j + i*65], i > j), which the LDL' left unused.
+    {
+        const int j = tid >> 2, part = tid & 3;
+        for (int i = 1; i < PB; ++i) {              // same trip count on every lane (full-mask shuffles)
+            double acc2 = 0.0;
+            if (i > j && i < nb)
+                for (int k = j + 1 + part; k < i; k += 4) acc2 += A[i + k * (PB + 1)] * A[j + k * (PB + 1)];
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+            if (part == 0 && i > j && i < nb) A[j + i * (PB + 1)] = -(A[i + j * (PB + 1)] + acc2);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // park [inv(L_JJ) strictly lower ; d on the diagonal] (column-major 64 x 64)
+    double* Wd = Wst + woff[blockIdx.x] + (int64_t)(J0 / PB) * (PB * PB);
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int i = e % PB, j = e / PB;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j < nb) { if (i > j) v = A[j + i * (PB + 1)]; else if (i == j) v = A[i + j * (PB + 1)]; }
+        Wd[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict__ Lst,
+         const double* __restrict__ Wst, const int64_t* __restrict__ woff,
+         const double* __restrict__ D, const double* __restrict__ Dinv) {
+    extern __shared__ double smem[];
+    double (*As)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem);
+    double (*Bs)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem + 2 * GBK * GBM);
+    double* Ts = smem + 4 * GBK * GBM;                // T: 64 rows x 65 (k index fastest -> [i][k])
+    double* Ms = Ts + PB * (PB + 1);                  // M[k][j], 64 x 65
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
     if (J0 >= ns) return;
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int r0 = J0 + blockIdx.x * GBM;
+    const int nb = min(PB, ns - J0);
+    const int r0 = J0 + nb + blockIdx.x * GBM;
     if (r0 >= nf) return;
     double* Lp = Lst + S.panel_off[s];
-    double acc[4][LNB / 16];
-    ldl_gemm_tile<LNB>(Lp, nf, D + f, r0, J0, 0, J0, acc, As, Bs);
-    const int nb = min(LNB, ns - J0);
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+    ldl_gemm_tile<GBM>(Lp, nf, D + f, r0, J0, 0, J0, acc, As, Bs);
+    if (J0 == 0) {
 #pragma unroll
-    for (int c = 0; c < LNB / 16; ++c) {
-        const int cj = ty * (LNB / 16) + c;
-        if (cj >= nb) continue;
-        double* col = Lp + (int64_t)(J0 + cj) * nf;
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = tx * 4 + a, k = ty * 4 + c;
+            const int gr = r0 + i;
+            Ts[i * (PB + 1) + k] = (gr < nf && k < nb) ? Lp[(int64_t)(J0 + k) * nf + gr] - acc[a][c] : 0.0;
+        }
+    const double* Wd = Wst + woff[blockIdx.y] + (int64_t)(J0 / PB) * (PB * PB);
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int jj = e % PB, kk = e / PB;          // Wd[jj + kk*PB] = inv(L_JJ)[jj][kk] (jj > kk)
+        double v = 0.0;
+        if (jj < nb && kk < nb) {
+            if (jj > kk) v = Wd[e] * Dinv[f + J0 + jj];
+            else if (jj == kk) v = Dinv[f + J0 + jj];
+        }
+        Ms[kk * (PB + 1) + jj] = v;                  // M[k][j] = inv(L)[j][k] * dinv[j], k <= j
+    }
+    __syncthreads();
+    // L[rows, J] = T * M : out[i][j] = sum_{k <= j} T[i][k] M[k][j]
+    double out[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[a][c] = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < PB; ++k) {
+        double tv[4], mv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tv[a] = Ts[(tx * 4 + a) * (PB + 1) + k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mv[c] = Ms[k * (PB + 1) + ty * 4 + c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[a][c] += tv[a] * mv[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int j = ty * 4 + c;
+        if (j >= nb) continue;
+        double* col = Lp + (int64_t)(J0 + j) * nf;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int gr = r0 + tx * 4 + a;
-            if (gr < nf && gr >= J0 + cj) col[gr] -= acc[a][c];
+            if (gr < nf) col[gr] = out[a][c];
         }
     }
 }
@@ -326,116 +459,25 @@ k_schur_large(DevSym S, const int32_t* __restrict__ batch, const double* __restr
     }
 }
 
-// grid (row tiles, nbatch), 128 threads.  Every CTA factors the nb x nb diagonal block in shared
-// memory (redundantly: no inter-CTA dependency), then solves its rows against it.  The factored
-// diagonal block is parked in `Wst` (siblings may still be reading the unfactored one).
-__global__ void __launch_bounds__(LTR)
-k_panel_large(DevSym S, const int32_t* __restrict__ batch, int kb, double* __restrict__ Lst,
-              double* __restrict__ Wst, const int64_t* __restrict__ woff,
-              double* __restrict__ D, double* __restrict__ Dinv, RegParams rp,
-              unsigned int* __restrict__ nreg) {
-    __shared__ double A[LNB][LNB + 1];
-    __shared__ double dv[LNB], dinvs[LNB];
-    const int s = batch[blockIdx.y];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    if (kb >= ns) return;
-    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int nf = ns + nr;
-    const int nb = min(LNB, ns - kb);
-    const int r0 = kb + nb + blockIdx.x * LTR;
-    if (r0 >= nf && blockIdx.x != 0) return;
-    double* Lp = Lst + S.panel_off[s];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < nb * nb; e += LTR) {
-        const int i = e % nb, j = e / nb;
-        A[i][j] = (i >= j) ? Lp[(int64_t)(kb + j) * nf + kb + i] : 0.0;
-    }
-    __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-        double d = A[k][k];
-        const double sg = (double)S.dsign[f + kb + k];
-        bool reg = false;
-        if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
-        const double dinv = 1.0 / d;
-        __syncthreads();
-        for (int e = tid; e < (nb - k - 1) * (nb - k - 1); e += LTR) {
-            const int i = k + 1 + e % (nb - k - 1), j = k + 1 + e / (nb - k - 1);
-            if (i >= j) A[i][j] -= A[i][k] * A[j][k] * dinv;
-        }
-        __syncthreads();
-        for (int i = k + 1 + tid; i < nb; i += LTR) A[i][k] *= dinv;
-        if (tid == 0) {
-            dv[k] = d; dinvs[k] = dinv;
-            if (blockIdx.x == 0 && reg) atomicAdd(nreg, 1u);
-        }
-        __syncthreads();
-    }
-    if (blockIdx.x == 0) {
-        double* Wd = Wst + woff[blockIdx.y] + (int64_t)(kb / LNB) * (LNB * LNB);
-        for (int e = tid; e < LNB * LNB; e += LTR) {
-            const int i = e % LNB, j = e / LNB;
-            Wd[e] = (i < nb && j < nb) ? (i > j ? A[i][j] : (i == j ? dv[j] : 0.0)) : 0.0;
-        }
-        for (int k = tid; k < nb; k += LTR) { D[f + kb + k] = dv[k]; Dinv[f + kb + k] = dinvs[k]; }
-    }
-    const int r = r0 + tid;
-    if (r < nf) {
-        double x[LNB];
-#pragma unroll
-        for (int j = 0; j < LNB; ++j) x[j] = (j < nb) ? Lp[(int64_t)(kb + j) * nf + r] : 0.0;
-#pragma unroll
-        for (int j = 0; j < LNB; ++j) {
-            if (j < nb) {
-                double v = x[j];
-#pragma unroll
-                for (int l = 0; l < LNB; ++l) if (l < j) v -= x[l] * A[j][l];
-                x[j] = v;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < LNB; ++j) if (j < nb) Lp[(int64_t)(kb + j) * nf + r] = x[j] * dinvs[j];
-    }
-}
-
-// Finish the large fronts of a level: bring the parked (factored) LNB x LNB diagonal blocks into
-// the panel and replace every SB x SB diagonal block of L11 by its inverse.
-// grid (max SB-blocks per front, nbatch), 64 threads, dynamic smem 2*SB*SB doubles.
-__global__ void __launch_bounds__(64)
+// Finish the large fronts of a level: copy the parked blocks [inv(L_JJ) strictly lower ; d on the
+// diagonal] into the panel (the solve kernels expect inverted SB x SB diagonal blocks, SB == PB).
+// grid (max blocks per front, nbatch), 256 threads.
+__global__ void __launch_bounds__(256)
 k_finish_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ Lst,
                const double* __restrict__ Wst, const int64_t* __restrict__ woff) {
-    extern __shared__ double T[];
-    double* buf = T + SB * SB;
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
-    const int kb = blockIdx.x * SB;
+    const int kb = blockIdx.x * PB;
     if (kb >= ns) return;
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int sb = min(SB, ns - kb);
+    const int sb = min(PB, ns - kb);
     double* Lp = Lst + S.panel_off[s] + (int64_t)kb * nf + kb;
-    const double* Wd = Wst + woff[blockIdx.y];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < sb * sb; e += 64) {
-        const int i = e % sb, j = e / sb;
-        const int bi = i / LNB, bj = j / LNB;
-        double v;
-        if (bi == bj) v = Wd[(int64_t)((kb / LNB) + bi) * (LNB * LNB) + (i % LNB) + (j % LNB) * LNB];
-        else v = Lp[i + (int64_t)j * nf];
-        T[i + j * SB] = v;
+    const double* Wd = Wst + woff[blockIdx.y] + (int64_t)blockIdx.x * (PB * PB);
+    for (int e = threadIdx.x; e < PB * PB; e += 256) {
+        const int i = e % PB, j = e / PB;
+        if (i < sb && j < sb && i >= j) Lp[i + (int64_t)j * nf] = Wd[e];
     }
-    __syncthreads();
-    // keep the pivots (diagonal of the parked blocks) aside: the panel diagonal holds D
-    for (int i = tid; i < sb; i += 64) buf[i] = T[i + i * SB];
-    __syncthreads();
-    double dsave = (tid < sb) ? buf[tid] : 0.0;
-    __syncthreads();
-    invert_unit_lower_block(T, SB, sb, buf, tid, 64);
-    for (int e = tid; e < sb * sb; e += 64) {
-        const int i = e % sb, j = e / sb;
-        if (i > j) Lp[i + (int64_t)j * nf] = T[i + j * SB];
-    }
-    if (tid < sb) Lp[tid + (int64_t)tid * nf] = dsave;
 }
 
 // ------------------------------------------------------------------ scatter / regularisation
