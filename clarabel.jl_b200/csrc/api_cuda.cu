@@ -378,9 +378,16 @@ int residual(cb200_handle* h, const double* d_xi, double* d_e, int slot) {
     h->tm.begin(Timers::SPMV, st);
     CUDA_OK(cudaMemsetAsync(h->d_scal.p + slot, 0, sizeof(unsigned long long), st));
     if (h->N) {
-        k_residual<<<nblk(h->N * 32, 256), 256, 0, st>>>(h->N, h->d_cp.p, h->d_ri.p, h->d_nz.p, h->d_tp.p,
-                                                         h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p, d_e,
-                                                         h->d_scal.p + slot);
+        // lanes per row chosen from the mean row length of the symmetric matrix
+        const double mean_row = 2.0 * (double)h->nnzK / (double)h->N;
+        if (mean_row > 48.0)
+            k_residual<32><<<nblk(h->N * 32, 256), 256, 0, st>>>(h->N, h->d_cp.p, h->d_ri.p, h->d_nz.p, h->d_tp.p,
+                                                                 h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p, d_e,
+                                                                 h->d_scal.p + slot);
+        else
+            k_residual<4><<<nblk(h->N * 4, 256), 256, 0, st>>>(h->N, h->d_cp.p, h->d_ri.p, h->d_nz.p, h->d_tp.p,
+                                                               h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p, d_e,
+                                                               h->d_scal.p + slot);
         LAUNCH(h);
     }
     h->tm.end(st);

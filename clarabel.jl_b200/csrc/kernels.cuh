@@ -596,7 +596,7 @@ __device__ __forceinline__ void cols8_dot(const double* __restrict__ base, int64
     }
 }
 
-// --- leaves with a single pivot column and no children: one thread per supernode
+// --- supernodes with a single pivot column and a short front: one thread per supernode
 __global__ void __launch_bounds__(128)
 k_fwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
            double* __restrict__ y, double* __restrict__ uvec) {
@@ -607,8 +607,21 @@ k_fwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double*
     const int64_t rp = S.rows_ptr[s];
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const double* Lp = Lst + S.panel_off[s];
-    const double x = y[f];
-    for (int i = 0; i < nr; ++i) uvec[rp + i] = -Lp[1 + i] * x;
+    if (S.child_ptr[s + 1] == S.child_ptr[s]) {          // true leaf: no contributions to gather
+        const double x = y[f];
+        for (int i = 0; i < nr; ++i) uvec[rp + i] = -Lp[1 + i] * x;
+        return;
+    }
+    const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+    const int64_t base = S.asm_base[s];
+    double x = y[f];
+    for (int e = cp[0]; e < cp[1]; ++e) x += uvec[S.asm_src[base + e]];
+    y[f] = x;
+    for (int i = 0; i < nr; ++i) {
+        double acc = 0.0;
+        for (int e = cp[1 + i]; e < cp[2 + i]; ++e) acc += uvec[S.asm_src[base + e]];
+        uvec[rp + i] = acc - Lp[1 + i] * x;
+    }
 }
 __global__ void __launch_bounds__(128)
 k_bwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
@@ -1020,28 +1033,34 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
 
 // ------------------------------------------------------------------ G8 residual e = b - K x
 // K symmetric, stored as upper CSC (cp, ri, nz) plus the row-wise index of the same entries
-// (tp, tc, tpos: entries (j, c > j) of row j, value nz[tpos]).  One warp per row.
+// (tp, tc, tpos: entries (j, c > j) of row j, value nz[tpos]).  RL lanes cooperate on one row
+// (KKT rows are short: ~5 + 5 entries; dense cone rows just loop), 256/RL rows per CTA.
+template <int RL>
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, const int64_t* __restrict__ cp, const int32_t* __restrict__ ri,
            const double* __restrict__ nz, const int64_t* __restrict__ tp,
            const int32_t* __restrict__ tc, const int64_t* __restrict__ tpos,
            const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ e,
            unsigned long long* __restrict__ norm_bits) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int sub = threadIdx.x % RL;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / RL;
     double r = 0.0;
+    double acc = 0.0;
     if (row < N) {
-        double acc = 0.0;
-        for (int64_t p = cp[row] + lane; p < cp[row + 1]; p += 32) acc += nz[p] * x[ri[p]];
-        for (int64_t p = tp[row] + lane; p < tp[row + 1]; p += 32) acc += nz[tpos[p]] * x[tc[p]];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        for (int64_t p = cp[row] + sub; p < cp[row + 1]; p += RL) acc += nz[p] * x[ri[p]];
+        for (int64_t p = tp[row] + sub; p < tp[row + 1]; p += RL) acc += nz[tpos[p]] * x[tc[p]];
+    }
+#pragma unroll
+    for (int o = RL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < N) {
         r = b[row] - acc;
-        if (lane == 0) e[row] = r;
+        if (sub == 0) e[row] = r;
     }
     double m = fabs(r);
     if (!(m == m)) m = __longlong_as_double(0x7ff0000000000000LL);   // NaN -> +inf
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ double sm[8];
-    if (lane == 0) sm[threadIdx.x >> 5] = m;
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
