@@ -6,6 +6,9 @@
 #include "api_common.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -51,6 +54,7 @@ struct LevelPlan {
     Batch small[NSMALL];
     Batch large;
     Batch solve[NSOLVE];
+    Batch topf, tops;          // multi-GPU: replicated top fronts of this level (factor / solve)
     int64_t wtotal = 0;        // doubles of W workspace needed by the large batch
 };
 
@@ -74,6 +78,50 @@ struct Timers {
     }
     ~Timers() { for (auto e : pool) cudaEventDestroy(e); }
 };
+
+// NCCL is bound at run time (dlsym): the library loads without NCCL for single-GPU use, and under
+// torchrun it resolves to the NCCL that torch already loaded.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    bool load() {
+        if (ok) return true;
+        void* hd = RTLD_DEFAULT;
+        auto sym = [&](const char* n) { return dlsym(hd, n); };
+        if (!sym("ncclAllReduce")) {
+            const char* names[] = {"libnccl.so.2", "libnccl.so"};
+            hd = nullptr;
+            for (const char* n : names) { hd = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (hd) break; }
+            if (!hd) return false;
+        }
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        ok = GetUniqueId && CommInitRank && AllReduce && GroupStart && GroupEnd && CommDestroy;
+        return ok;
+    }
+};
+static NcclApi g_nccl;
+
+#define NCCL_OK(call)                                                                      \
+    do {                                                                                   \
+        ncclResult_t _r = (call);                                                          \
+        if (_r != ncclSuccess) {                                                           \
+            set_error(std::string(#call) + ": " +                                          \
+                      (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error")); \
+            return -200 - (int)_r;                                                         \
+        }                                                                                  \
+    } while (0)
 
 struct GraphExec {
     cudaGraphExec_t exec = nullptr;
@@ -133,6 +181,14 @@ struct cb200_handle {
     DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
     double last_eps = 0;
     bool resident = false;
+    // multi-GPU state
+    bool dist = false; int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    std::vector<int32_t> owner; std::vector<int8_t> is_top;
+    std::vector<int32_t> h_top_list;
+    std::vector<std::vector<int32_t>> h_top_by_level;
+    DevBuf<int8_t> d_active, d_keepcol, d_topcolkeep;
+    DevBuf<int32_t> d_top_list;
     GraphExec g_factor[2], g_solve;     // CUDA graphs: factor (without/with static reg), solve sweeps
     Timers tm;
 };
@@ -146,6 +202,7 @@ DevSym devsym(cb200_handle* h) {
     d.panel_off = h->d_panel_off.p; d.upd_off = h->d_upd_off.p; d.dsign = h->d_dsign_perm.p;
     d.front_ptr = h->d_front_ptr.p; d.asm_base = h->d_asm_base.p; d.asm_colptr = h->d_asm_colptr.p;
     d.asm_src = h->d_asm_src.p; d.asm_child = h->d_asm_child.p;
+    d.active = h->dist ? h->d_active.p : nullptr;
     return d;
 }
 
@@ -165,7 +222,7 @@ int launch_small(cb200_handle* h, const Batch& b, int nfcap, RegParams rp) {
     return 0;
 }
 
-void launch_fwd_level(cb200_handle* h, const LevelPlan& P) {
+void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     DevSym ds = devsym(h);
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
@@ -185,11 +242,26 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P) {
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
     }
-    const Batch& b3 = P.solve[3];
-    if (b3.cnt) {
+    for (int pass = 0; pass < 2; ++pass) {
+        const Batch& b3 = pass == 0 ? P.solve[3] : P.tops;
+        if (!b3.cnt) continue;
         const int32_t* bl = h->d_batches.p + b3.off;
         k_big_asm_fwd<<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        if (pass == 1 && h->dist) {
+            // sum the per-rank partial right-hand sides of the replicated top fronts
+            const Symbolic& S = h->S;
+            g_nccl.GroupStart();
+            for (int32_t sn : h->h_top_by_level[lv]) {
+                double* yt = h->d_y.p + S.sn_first[sn];
+                g_nccl.AllReduce(yt, yt, (size_t)S.ns(sn), ncclDouble, ncclSum, h->comm, h->stream);
+                if (S.nr(sn) > 0) {
+                    double* ut = h->d_uvec.p + S.rows_ptr[sn];
+                    g_nccl.AllReduce(ut, ut, (size_t)S.nr(sn), ncclDouble, ncclSum, h->comm, h->stream);
+                }
+            }
+            g_nccl.GroupEnd();
+        }
         const int npanel = nblk(b3.maxns, WP);
         for (int pk = 0; pk < npanel; ++pk) {
             k_big_tri_fwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, h->d_L.p, h->d_y.p);
@@ -205,8 +277,9 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P) {
 }
 void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     DevSym ds = devsym(h);
-    const Batch& b3 = P.solve[3];
-    if (b3.cnt) {
+    for (int pass = 0; pass < 2; ++pass) {
+        const Batch& b3 = pass == 0 ? P.tops : P.solve[3];
+        if (!b3.cnt) continue;
         const int32_t* bl = h->d_batches.p + b3.off;
         const int npanel = nblk(b3.maxns, WP);
         const int maxtiles = std::max(1, nblk(b3.maxnf, BRT));
@@ -240,6 +313,82 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
                                                              h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
     }
+}
+
+
+// Builds the per-level launch plans.  In multi-GPU mode a rank only schedules the supernodes it
+// owns plus the replicated top fronts (which always take the large-front / big-solve paths so
+// that assembly, all-reduce and factorisation are separate steps).
+int build_plans(cb200_handle* h) {
+    const Symbolic& S = h->S;
+    cudaStream_t s = h->stream;
+    h->plan.assign(S.nlevels, LevelPlan());
+    std::vector<int32_t> batches; std::vector<int64_t> woff;
+    int64_t wmax = 0;
+    auto add_batch = [&](Batch& b, const std::vector<int32_t>& v, bool large, LevelPlan& P) {
+        b = Batch();
+        b.off = (int32_t)batches.size(); b.cnt = (int32_t)v.size();
+        int64_t w = 0;
+        for (int32_t sn : v) {
+            int nf = S.ns(sn) + S.nr(sn);
+            b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
+            b.maxnr = std::max(b.maxnr, S.nr(sn));
+            batches.push_back(sn);
+            woff.push_back(large ? w : 0);
+            if (large) w += (int64_t)nblk(S.ns(sn), PB) * PB * PB;   // parked diagonal blocks
+        }
+        if (large) { P.wtotal += w; wmax = std::max(wmax, w); }
+    };
+    for (int lv = 0; lv < S.nlevels; ++lv) {
+        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], top;
+        for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
+            int32_t sn = S.level_list[q];
+            if (h->dist) {
+                if (h->is_top[sn]) { top.push_back(sn); continue; }
+                if (h->owner[sn] != h->rank) continue;
+            }
+            int nf = S.ns(sn) + S.nr(sn);
+            int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
+            cls[c].push_back(sn);
+            const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
+            const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
+            const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2));
+            scl[d].push_back(sn);
+        }
+        LevelPlan& P = h->plan[lv];
+        P.wtotal = 0;
+        for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
+        add_batch(P.large, cls[NSMALL], true, P);
+        for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
+        add_batch(P.topf, top, true, P);
+        add_batch(P.tops, top, false, P);
+    }
+    CUDA_OK(h->d_batches.upload(batches, s)); CUDA_OK(h->d_woff.upload(woff, s));
+    CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
+    size_t pmax = 1;
+    for (const LevelPlan& P : h->plan)
+        for (const Batch* b3 : {&P.solve[3], &P.tops})
+            if (b3->cnt) pmax = std::max(pmax, (size_t)b3->cnt * std::max(1, nblk(b3->maxnf, BRT)) * WP);
+    CUDA_OK(h->d_partial.alloc(pmax));
+    return 0;
+}
+
+// all-reduce (sum) of the panel and update block of every front of a batch, one NCCL group
+int allreduce_fronts(cb200_handle* h, const Batch& B, const std::vector<int32_t>& list) {
+    const Symbolic& S = h->S;
+    NCCL_OK(g_nccl.GroupStart());
+    for (int32_t k = 0; k < B.cnt; ++k) {
+        const int32_t sn = list[k];
+        const int64_t ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
+        double* Lp = h->d_L.p + S.panel_off[sn];
+        NCCL_OK(g_nccl.AllReduce(Lp, Lp, (size_t)(nf * ns), ncclDouble, ncclSum, h->comm, h->stream));
+        if (nr > 0) {
+            double* Us = h->d_U.p + S.upd_off[sn];
+            NCCL_OK(g_nccl.AllReduce(Us, Us, (size_t)(nr * nr), ncclDouble, ncclSum, h->comm, h->stream));
+        }
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    return 0;
 }
 
 // zero the update blocks of the large fronts of one level
@@ -298,6 +447,11 @@ int factor_body(cb200_handle* h, bool static_reg) {
     RegParams rp{h->st.dynamic_regularization_eps, h->st.dynamic_regularization_delta,
                  h->st.dynamic_regularization_enable};
     DevSym ds = devsym(h);
+    if (h->dist && h->rank != 0 && !h->h_top_list.empty()) {
+        // the original entries of the replicated top fronts are contributed by rank 0 only
+        k_zero_panels<<<dim3(32, (unsigned)h->h_top_list.size()), 256, 0, st>>>(ds, h->d_top_list.p, h->d_L.p);
+        LAUNCH(h);
+    }
     for (int lv = 0; lv < S.nlevels; ++lv) {
         const LevelPlan& P = h->plan[lv];
         launch_small<32>(h, P.small[0], 16, rp);
@@ -306,14 +460,22 @@ int factor_body(cb200_handle* h, bool static_reg) {
         launch_small<256>(h, P.small[3], 96, rp);
         launch_small<256>(h, P.small[4], 128, rp);
         launch_small<256>(h, P.small[5], 160, rp);
-        const Batch& B = P.large;
-        if (B.cnt) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const Batch& B = pass == 0 ? P.large : P.topf;
+            if (!B.cnt) continue;
+            const bool is_top = pass == 1;
             const int32_t* bl = h->d_batches.p + B.off;
             const int64_t* wo = h->d_woff.p + B.off;
-            int maxnr = B.maxnf;   // upper bound
-            k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)maxnr * maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
+            k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)B.maxnr * B.maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
             k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
             h->tm.nlaunch += 2;
+            if (is_top && h->dist) {
+                // root-front assembly across GPUs: every rank holds the contributions of its own
+                // subtrees (rank 0 also the original entries); sum them over NVLink.
+                std::vector<int32_t> list(h->h_top_by_level[lv]);
+                int rc = allreduce_fronts(h, B, list);
+                if (rc) return rc;
+            }
             const size_t sm64 = (size_t)(4 * GBK * GBM + 2 * PB * (PB + 1)) * sizeof(double);
             for (int kb = 0; kb < B.maxns; kb += PB) {
                 k_diag64<<<B.cnt, 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
@@ -333,8 +495,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                     LAUNCH(h);
                 }
             }
-            k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(
-                ds, bl, h->d_L.p, h->d_W.p, wo);
+            k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
     }
@@ -353,7 +514,7 @@ int factor(cb200_handle* h, bool static_reg) {
 // y (permuted, in d_y) <- K^-1 : forward, diagonal, backward
 int sweeps_body(cb200_handle* h) {
     const auto& S = h->S;
-    for (int lv = 0; lv < S.nlevels; ++lv) launch_fwd_level(h, h->plan[lv]);
+    for (int lv = 0; lv < S.nlevels; ++lv) launch_fwd_level(h, h->plan[lv], lv);
     for (int lv = S.nlevels - 1; lv >= 0; --lv) launch_bwd_level(h, h->plan[lv]);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -363,8 +524,18 @@ int tri_solve(cb200_handle* h, const double* d_rhs, double* d_sol) {
     cudaStream_t st = h->stream;
     h->tm.begin(Timers::SOLVE, st);
     if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
+    if (h->dist && h->N) {
+        // top-front entries of the right-hand side are contributed by rank 0 only
+        k_mask_vec<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_topcolkeep.p, h->N); LAUNCH(h);
+    }
     int rc = run_captured(h, h->g_solve, [&]() { return sweeps_body(h); });
     if (rc) return rc;
+    if (h->dist && h->N) {
+        // every rank holds the solution on its own subtrees (+ the replicated top part): gather by
+        // zeroing what a rank does not own and summing over NVLink
+        k_mask_vec<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_keepcol.p, h->N); LAUNCH(h);
+        NCCL_OK(g_nccl.AllReduce(h->d_y.p, h->d_y.p, (size_t)h->N, ncclDouble, ncclSum, h->comm, st));
+    }
     if (h->N) { k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h); }
     h->tm.end(st);
     h->tm.nsolve += 1;
@@ -469,55 +640,15 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_front_ptr.upload(S.front_ptr, s)); CUDA_OK(h->d_asm_base.upload(S.asm_base, s));
         CUDA_OK(h->d_asm_colptr.upload(S.asm_colptr, s)); CUDA_OK(h->d_asm_src.upload(S.asm_src, s));
         CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
-        // ---- level plans
-        h->plan.assign(S.nlevels, LevelPlan());
-        std::vector<int32_t> batches; std::vector<int64_t> woff;
-        int64_t wmax = 0;
-        auto add_batch = [&](Batch& b, const std::vector<int32_t>& v, bool large, LevelPlan& P) {
-            b.off = (int32_t)batches.size(); b.cnt = (int32_t)v.size();
-            int64_t w = 0;
-            for (int32_t sn : v) {
-                int nf = S.ns(sn) + S.nr(sn);
-                b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
-                b.maxnr = std::max(b.maxnr, S.nr(sn));
-                batches.push_back(sn);
-                woff.push_back(large ? w : 0);
-                if (large) w += (int64_t)nblk(S.ns(sn), PB) * PB * PB;   // parked diagonal blocks
-            }
-            if (large) { P.wtotal = w; wmax = std::max(wmax, w); }
-        };
-        for (int lv = 0; lv < S.nlevels; ++lv) {
-            std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE];
-            for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
-                int32_t sn = S.level_list[q];
-                int nf = S.ns(sn) + S.nr(sn);
-                int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
-                cls[c].push_back(sn);
-                const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
-                const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
-                const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2));
-                scl[d].push_back(sn);
-            }
-            LevelPlan& P = h->plan[lv];
-            for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
-            add_batch(P.large, cls[NSMALL], true, P);
-            for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
-        }
-        CUDA_OK(h->d_batches.upload(batches, s)); CUDA_OK(h->d_woff.upload(woff, s));
+        // ---- level plans (+ workspace sized for them)
+        { int rcp = build_plans(h); if (rcp) { delete h; return rcp; } }
         // ---- numeric storage
         CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
         CUDA_OK(h->d_U.alloc((size_t)std::max<int64_t>(1, S.upd_total)));
-        CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
         CUDA_OK(h->d_D.alloc(N)); CUDA_OK(h->d_Dinv.alloc(N));
+        if (N) { CUDA_OK(cudaMemsetAsync(h->d_D.p, 0, N * sizeof(double), s)); CUDA_OK(cudaMemsetAsync(h->d_Dinv.p, 0, N * sizeof(double), s)); }
         CUDA_OK(h->d_uvec.alloc(std::max<size_t>(1, S.rows.size())));
-        {
-            size_t pmax = 1;
-            for (const LevelPlan& P : h->plan) {
-                const Batch& b3 = P.solve[3];
-                if (b3.cnt) pmax = std::max(pmax, (size_t)b3.cnt * std::max(1, nblk(b3.maxnf, BRT)) * WP);
-            }
-            CUDA_OK(h->d_partial.alloc(pmax));
-        }
+
         for (DevBuf<double>* b : {&h->d_b, &h->d_x, &h->d_e, &h->d_dx, &h->d_y}) {
             CUDA_OK(b->alloc(std::max<int64_t>(1, N)));
             CUDA_OK(cudaMemsetAsync(b->p, 0, std::max<int64_t>(1, N) * sizeof(double), s));
@@ -548,6 +679,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
 void cb200_destroy(cb200_handle* h) {
     if (!h) return;
     if (h->stream) { cudaStreamSynchronize(h->stream); }
+    if (h->comm && g_nccl.ok) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     cudaStream_t s = h->stream;
     delete h;
     if (s) cudaStreamDestroy(s);
@@ -608,7 +740,7 @@ int32_t cb200_solve(cb200_handle* h, double* x, const double* b) {
 int32_t cb200_info(const cb200_handle* h, int64_t* nnzA, int64_t* nnzL, int32_t* ngpus) {
     if (nnzA) *nnzA = h->nnzK;
     if (nnzL) *nnzL = h->S.nnzL;
-    if (ngpus) *ngpus = 1;
+    if (ngpus) *ngpus = h->nranks;
     return 0;
 }
 
@@ -853,6 +985,60 @@ int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len) {
     for (int i = 0; i < len && i < 7; ++i) out[i] = v[i];
     return 0;
 }
+int32_t cb200_nccl_unique_id(char out[128]) {
+    if (!g_nccl.load()) { set_error("NCCL library not found (dlopen libnccl.so.2)"); return -5; }
+    ncclUniqueId id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    std::memcpy(out, &id, 128);
+    return 0;
+}
+
+int32_t cb200_dist_init(cb200_handle* h, int32_t rank, int32_t nranks, const char uid[128]) {
+    try {
+        if (nranks <= 1) return 0;
+        if (!g_nccl.load()) { set_error("NCCL library not found (dlopen libnccl.so.2)"); return -5; }
+        CUDA_OK(cudaSetDevice(h->st.device));
+        ncclUniqueId id; std::memcpy(&id, uid, 128);
+        NCCL_OK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+        h->rank = rank; h->nranks = nranks; h->dist = true;
+        const Symbolic& S = h->S;
+        partition_subtrees(S, nranks, h->owner, h->is_top);
+        h->h_top_list.clear(); h->h_top_by_level.assign(S.nlevels, {});
+        for (int lv = 0; lv < S.nlevels; ++lv)
+            for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
+                const int32_t sn = S.level_list[q];
+                if (h->is_top[sn]) { h->h_top_list.push_back(sn); h->h_top_by_level[lv].push_back(sn); }
+            }
+        std::vector<int8_t> active(S.nsuper), keep(S.N), topkeep(S.N);
+        for (int32_t sn = 0; sn < S.nsuper; ++sn) {
+            const bool top = h->is_top[sn];
+            active[sn] = top ? (rank == 0) : (h->owner[sn] == rank);
+            const int8_t kc = top ? (rank == 0) : (h->owner[sn] == rank);
+            for (int32_t j = S.sn_first[sn]; j < S.sn_first[sn + 1]; ++j) {
+                keep[j] = kc;
+                topkeep[j] = top ? (rank == 0) : 1;
+            }
+        }
+        cudaStream_t s = h->stream;
+        CUDA_OK(h->d_active.upload(active, s)); CUDA_OK(h->d_keepcol.upload(keep, s));
+        CUDA_OK(h->d_topcolkeep.upload(topkeep, s)); CUDA_OK(h->d_top_list.upload(h->h_top_list, s));
+        // update blocks of supernodes other ranks own are never written here: keep them zero
+        CUDA_OK(cudaMemsetAsync(h->d_U.p, 0, h->d_U.n * sizeof(double), s));
+        int rc = build_plans(h);
+        if (rc) return rc;
+        // the captured launch sequences (if any) belong to the single-GPU plans
+        for (GraphExec* g : {&h->g_factor[0], &h->g_factor[1], &h->g_solve}) {
+            if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+            g->failed = false;
+        }
+        const char* env = getenv("CB200_DIST_GRAPH");
+        if (!(env && env[0] == '1')) h->st.use_cuda_graph = 0;   // NCCL inside stream capture: opt-in
+        CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
 void* cb200_get_stream(cb200_handle* h) { return (void*)h->stream; }
 int32_t cb200_set_resident(cb200_handle* h, int32_t resident) { h->resident = resident != 0; return 0; }
 int32_t cb200_reset_timers(cb200_handle* h) {

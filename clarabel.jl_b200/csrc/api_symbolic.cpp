@@ -84,6 +84,15 @@ int64_t cb200_symbolic_stat(const cb200_symbolic* s, int32_t what) {
 }
 double cb200_symbolic_flops(const cb200_symbolic* s) { return s->S.flops; }
 
+int32_t cb200_symbolic_partition(const cb200_symbolic* s, int32_t nranks, int64_t* owner,
+                                 int64_t* is_top, double* rank_load) {
+    std::vector<int32_t> ow; std::vector<int8_t> tp; std::vector<double> ld;
+    cb200::partition_subtrees(s->S, nranks, ow, tp, &ld);
+    for (size_t i = 0; i < ow.size(); ++i) { owner[i] = ow[i]; is_top[i] = tp[i]; }
+    if (rank_load) for (size_t i = 0; i < ld.size(); ++i) rank_load[i] = ld[i];
+    return 0;
+}
+
 int32_t cb200_symbolic_get(const cb200_symbolic* s, int32_t which, int64_t* out, int64_t len) {
     const auto& S = s->S;
     switch (which) {

@@ -30,6 +30,8 @@ struct DevSym {                 // device copies of the Symbolic arrays
     const int32_t* asm_colptr;
     const int32_t* asm_src;
     const int32_t* asm_child;
+    const int8_t*  active;      // multi-GPU: per-supernode mask of children whose contributions this rank
+                                // assembles into the replicated top fronts (nullptr = all)
 };
 
 struct RegParams { double eps, delta; int enable; };
@@ -171,6 +173,7 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
     for (int e = cp[d]; e < cp[d + 1]; ++e) {
         const int q = S.asm_src[base + e];
         const int c = S.asm_child[base + e];
+        if (S.active && !S.active[c]) continue;
         const int64_t rp0 = S.rows_ptr[c];
         const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
         const int j = (int)(q - rp0);
@@ -845,7 +848,8 @@ k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ 
     const int32_t* cp = S.asm_colptr + S.front_ptr[s];
     const int64_t base = S.asm_base[s];
     double acc = i < ns ? y[f + i] : 0.0;
-    for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+    for (int e = cp[i]; e < cp[i + 1]; ++e)
+        if (!S.active || S.active[S.asm_child[base + e]]) acc += uvec[S.asm_src[base + e]];
     if (i < ns) y[f + i] = acc; else uvec[rp + i - ns] = acc;
 }
 
@@ -1079,6 +1083,20 @@ __global__ void k_absmax(const double* __restrict__ v, int64_t n, unsigned long 
     }
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// multi-GPU helpers: zero the panels of a list of supernodes / zero or mask entries of y
+__global__ void k_zero_panels(DevSym S, const int32_t* __restrict__ list, double* __restrict__ Lst) {
+    const int s = list[blockIdx.y];
+    const int64_t ns = S.sn_first[s + 1] - S.sn_first[s];
+    const int64_t nf = ns + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    double* Lp = Lst + S.panel_off[s];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nf * ns;
+         i += (int64_t)gridDim.x * blockDim.x) Lp[i] = 0.0;
+}
+__global__ void k_mask_vec(double* __restrict__ y, const int8_t* __restrict__ keep, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && !keep[i]) y[i] = 0.0;
 }
 
 __global__ void k_axpy1(double* __restrict__ dx, const double* __restrict__ x, int64_t n) {

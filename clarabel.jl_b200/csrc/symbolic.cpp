@@ -378,4 +378,59 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
     }
 }
 
+void partition_subtrees(const Symbolic& S, int32_t nranks, std::vector<int32_t>& owner,
+                        std::vector<int8_t>& is_top, std::vector<double>* rank_load) {
+    const int32_t n = S.nsuper;
+    owner.assign(n, 0); is_top.assign(n, 0);
+    if (rank_load) rank_load->assign(std::max(1, nranks), 0.0);
+    if (n == 0) return;
+    // subtree weights (factor flops of the front, accumulated upwards; children precede parents)
+    std::vector<double> wself(n), wsub(n);
+    for (int32_t s = 0; s < n; ++s) {
+        const double w = S.ns(s), nf = w + S.nr(s);
+        wself[s] = w * nf * nf + 1.0;
+        wsub[s] = wself[s];
+    }
+    for (int32_t s = 0; s < n; ++s) if (S.sn_parent[s] >= 0) wsub[S.sn_parent[s]] += wsub[s];
+    double total = 0;
+    std::vector<int32_t> cand;                       // roots of the current subtree forest
+    for (int32_t s = 0; s < n; ++s) if (S.sn_parent[s] < 0) { cand.push_back(s); total += wsub[s]; }
+    if (nranks <= 1) return;
+    // Grow the top set: repeatedly move the heaviest candidate root into it (exposing its children)
+    // until there are enough subtrees to balance: heaviest <= total / (2 * nranks) or nothing to split.
+    auto heavier = [&](int32_t a, int32_t b) { return wsub[a] < wsub[b]; };
+    std::make_heap(cand.begin(), cand.end(), heavier);
+    double top_w = 0;
+    while (!cand.empty()) {
+        const int32_t h = cand.front();
+        const bool need_more = (int32_t)cand.size() < 2 * nranks;
+        const bool too_heavy = wsub[h] > (total - top_w) / (1.5 * nranks);
+        if (!(need_more || too_heavy)) break;
+        if (S.child_ptr[h + 1] == S.child_ptr[h]) break;        // a leaf: cannot split further
+        if (top_w + wself[h] > 0.5 * total && !need_more) break; // do not replicate most of the work
+        std::pop_heap(cand.begin(), cand.end(), heavier); cand.pop_back();
+        is_top[h] = 1; top_w += wself[h];
+        for (int32_t q = S.child_ptr[h]; q < S.child_ptr[h + 1]; ++q) {
+            cand.push_back(S.child_list[q]);
+            std::push_heap(cand.begin(), cand.end(), heavier);
+        }
+    }
+    // LPT assignment of whole subtrees
+    std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return wsub[a] > wsub[b] || (wsub[a] == wsub[b] && a < b); });
+    std::vector<double> load(nranks, 0.0);
+    std::vector<int32_t> root_owner(n, -1);
+    for (int32_t r : cand) {
+        int32_t best = 0;
+        for (int32_t k = 1; k < nranks; ++k) if (load[k] < load[best]) best = k;
+        root_owner[r] = best; load[best] += wsub[r];
+    }
+    // propagate ownership down (parents have larger indices than children)
+    for (int32_t s = n - 1; s >= 0; --s) {
+        if (is_top[s]) { owner[s] = -1; continue; }
+        if (root_owner[s] >= 0) owner[s] = root_owner[s];
+        else owner[s] = owner[S.sn_parent[s]];
+    }
+    if (rank_load) *rank_load = load;
+}
+
 }  // namespace cb200

@@ -58,6 +58,13 @@ struct Symbolic {
     inline int32_t nr(int32_t s) const { return (int32_t)(rows_ptr[s + 1] - rows_ptr[s]); }
 };
 
+// Multi-GPU partition of the assembly tree: an upward-closed "top" set of
+// supernodes (root separator fronts) is replicated on every rank; the subtrees hanging below it
+// are independent and are assigned whole to ranks (longest-processing-time-first on factor flops).
+//   owner[s] in [0, nranks) for subtree supernodes, -1 for top supernodes ; is_top[s] in {0,1}
+void partition_subtrees(const Symbolic& S, int32_t nranks, std::vector<int32_t>& owner,
+                        std::vector<int8_t>& is_top, std::vector<double>* rank_load = nullptr);
+
 // colptr/rowval: upper-triangular CSC pattern (0-based) of the N x N KKT matrix.
 // user_perm (optional, length N): use this ordering instead of computing one.
 void symbolic_analyze(int64_t N, const int64_t* colptr, const int64_t* rowval,

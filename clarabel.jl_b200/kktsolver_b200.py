@@ -15,6 +15,7 @@ plugin registry: directldl_defaults.jl:1-72), kept so that the stock DirectLDLKK
 update_values!/scale_values!/refactor!/solve! exactly as it drives QDLDL.
 """
 import ctypes as C
+import os
 import numpy as np
 
 from . import lib as _lib
@@ -101,11 +102,31 @@ class B200DirectLDLSolver:
     def reset_timers(self):
         self._L.cb200_reset_timers(self._h)
 
+    def dist_init(self, rank, nranks, uid):
+        """Multi-GPU: join the NCCL communicator (uid: 128 bytes from nccl_unique_id() on rank 0)."""
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _lib.check(self._L.cb200_dist_init(self._h, int(rank), int(nranks), buf), "cb200_dist_init")
+
     def stream_ptr(self):
         return self._L.cb200_get_stream(self._h)
 
     def set_resident(self, flag):
         self._L.cb200_set_resident(self._h, int(bool(flag)))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().cb200_nccl_unique_id(buf), "cb200_nccl_unique_id")
+    return bytes(buf.raw)
+
+
+def dist_init_from_torch(ldl):
+    """Join all ranks of the default torch.distributed group (one process per GPU)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    obj = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    ldl.dist_init(rank, world, obj[0])
 
 
 class B200KKTSolver:
@@ -128,7 +149,17 @@ class B200KKTSolver:
             from .cones import PSD
             has_psd = bool(((cones.types == PSD) & (cones.dims > 2)).any())
             cs_over = dict(cs_over, ordering=0 if has_psd else 1)
+        if "device" not in cs_over:
+            cs_over = dict(cs_over, device=int(os.environ.get("LOCAL_RANK", "0")))
         self.ldl = B200DirectLDLSolver(self.KKT, self.Dsigns, settings, **cs_over)
+        # one process per GPU: if the caller runs under torch.distributed, shard the elimination
+        # tree over the ranks (every rank must then make the same calls with the same inputs)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist_init_from_torch(self.ldl)
+        except ImportError:
+            pass
         L, h = self.ldl._L, self.ldl._h
         mp = self.map
         ctype = np.ascontiguousarray(cones.types, dtype=np.int32)

@@ -21,6 +21,7 @@ EXPORTED = [
     "cb200_set_maps", "cb200_update_cones", "cb200_solve_ir", "cb200_update_P", "cb200_update_A",
     "cb200_download", "cb200_get_timers", "cb200_reset_timers", "cb200_last_error",
     "cb200_get_stream", "cb200_set_resident",
+    "cb200_symbolic_partition", "cb200_nccl_unique_id", "cb200_dist_init",
 ]
 
 
@@ -78,6 +79,9 @@ def lib():
         L.cb200_last_error.restype = C.c_char_p
         L.cb200_get_stream.argtypes = [P]; L.cb200_get_stream.restype = C.c_void_p
         L.cb200_set_resident.argtypes = [P, I32]; L.cb200_set_resident.restype = I32
+        L.cb200_symbolic_partition.argtypes = [P, I32, P, P, P]; L.cb200_symbolic_partition.restype = I32
+        L.cb200_nccl_unique_id.argtypes = [P]; L.cb200_nccl_unique_id.restype = I32
+        L.cb200_dist_init.argtypes = [P, I32, I32, P]; L.cb200_dist_init.restype = I32
         _LIB = L
     return _LIB
 
@@ -152,6 +156,14 @@ class Symbolic:
                 ch[par].append(sn)
         out["children"] = ch
         return out
+
+    def partition(self, nranks):
+        n = self.stats["nsuper"]
+        owner = np.empty(n, dtype=np.int64); top = np.empty(n, dtype=np.int64)
+        load = np.zeros(max(1, nranks))
+        check(lib().cb200_symbolic_partition(self._h, int(nranks), _p(owner), _p(top), _p(load)),
+              "cb200_symbolic_partition")
+        return owner, top.astype(bool), load
 
     def __del__(self):
         try:

@@ -70,6 +70,11 @@ double  cb200_symbolic_flops(const cb200_symbolic* s);
  * All arrays are returned widened to int64 into caller storage of the stated length. */
 int32_t cb200_symbolic_get(const cb200_symbolic* s, int32_t which, int64_t* out, int64_t len);
 
+/* Multi-GPU partition of the assembly tree (host-only): owner[s] in [0,nranks) or -1 for the
+ * replicated top set, is_top[s] in {0,1}, rank_load[nranks] = factor-flop weight per rank. */
+int32_t cb200_symbolic_partition(const cb200_symbolic* s, int32_t nranks, int64_t* owner,
+                                 int64_t* is_top, double* rank_load);
+
 /* Fill-reducing orderings (perm[k] = original index of the k-th pivot). */
 int32_t cb200_order_amd(int64_t n, const int64_t* colptr, const int64_t* rowval,
                         double dense_scale, int64_t* perm);
@@ -127,6 +132,16 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len);
  * 1 factor, 2 triangular solves, 3 spmv/residual ; counters: 4 #factor, 5 #solves, 6 #kernel launches */
 int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len);
 int32_t cb200_reset_timers(cb200_handle* h);
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU)
+ * Every rank creates the same handle on its own device (replicated symbolic analysis), then
+ * calls cb200_dist_init with a NCCL unique id obtained on rank 0 (cb200_nccl_unique_id) and
+ * distributed by the caller (torch.distributed / MPI).  Independent elimination-tree subtrees
+ * are factored and solved on their owner rank; the replicated top (root separator) fronts are
+ * assembled with an NCCL all-reduce over NVLink.  All ranks must then issue the same sequence
+ * of refactor / update_cones / solve calls with the same inputs; results are replicated. */
+int32_t cb200_nccl_unique_id(char out[128]);
+int32_t cb200_dist_init(cb200_handle* h, int32_t rank, int32_t nranks, const char uid[128]);
+
 /* The CUDA stream (cudaStream_t) all of this handle's work is enqueued on, so a caller can
  * bracket calls with its own events. */
 void*   cb200_get_stream(cb200_handle* h);
