@@ -46,7 +46,7 @@ void cb200_default_settings(cb200_settings* s) {
     s->iterative_refinement_abstol = 1e-12;
     s->iterative_refinement_max_iter = 10;
     s->iterative_refinement_stop_ratio = 5.0;
-    s->ordering = 1; s->amd_dense_scale = 1.5; s->nd_leaf_size = 96;
+    s->ordering = 1; s->amd_dense_scale = 0.3; s->nd_leaf_size = 96;
     s->use_cuda_graph = 1;
 }
 

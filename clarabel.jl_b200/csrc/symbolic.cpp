@@ -29,6 +29,59 @@ void etree_upper(int32_t n, const std::vector<int64_t>& up, const std::vector<in
         }
 }
 
+
+// Factor cost (sum of squared column lengths) of the ordering ip (ip[orig] = position), with an
+// early exit once `limit` is exceeded.  Used to arbitrate between the nested-dissection and the
+// AMD-class ordering: BFS level-structure separators are poor on expander-like KKT graphs.
+double ordering_cost(int32_t N, const int64_t* colptr, const int64_t* rowval,
+                     const std::vector<int32_t>& ip, double limit, bool* aborted) {
+    std::vector<int64_t> up(N + 1, 0), lp(N + 1, 0);
+    for (int32_t j = 0; j < N; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t a = ip[rowval[p]], b = ip[j];
+            if (a == b) continue;
+            up[std::max(a, b) + 1]++; lp[std::min(a, b) + 1]++;
+        }
+    for (int32_t j = 0; j < N; ++j) { up[j + 1] += up[j]; lp[j + 1] += lp[j]; }
+    std::vector<int32_t> ui(up[N]), li(lp[N]);
+    {
+        std::vector<int64_t> pu(up.begin(), up.end() - 1), pl(lp.begin(), lp.end() - 1);
+        for (int32_t j = 0; j < N; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t a = ip[rowval[p]], b = ip[j];
+                if (a == b) continue;
+                int32_t lo = std::min(a, b), hi = std::max(a, b);
+                ui[pu[hi]++] = lo; li[pl[lo]++] = hi;
+            }
+    }
+    std::vector<int32_t> parent;
+    etree_upper(N, up, ui, parent);
+    std::vector<int32_t> cptr(N + 1, 0), clist(N);
+    for (int32_t j = 0; j < N; ++j) if (parent[j] >= 0) cptr[parent[j] + 1]++;
+    for (int32_t j = 0; j < N; ++j) cptr[j + 1] += cptr[j];
+    { std::vector<int32_t> pos(cptr.begin(), cptr.end() - 1);
+      for (int32_t j = 0; j < N; ++j) if (parent[j] >= 0) clist[pos[parent[j]]++] = j; }
+    std::vector<std::vector<int32_t>> lists(N);
+    std::vector<int32_t> mark(N, -1);
+    double flops = 0;
+    *aborted = false;
+    for (int32_t j = 0; j < N; ++j) {
+        auto& L = lists[j];
+        mark[j] = j;
+        for (int64_t p = lp[j]; p < lp[j + 1]; ++p) { int32_t i = li[p]; if (mark[i] != j) { mark[i] = j; L.push_back(i); } }
+        for (int32_t q = cptr[j]; q < cptr[j + 1]; ++q) {
+            auto& C = lists[clist[q]];
+            for (int32_t i : C) if (mark[i] != j) { mark[i] = j; L.push_back(i); }
+            std::vector<int32_t>().swap(C);
+        }
+        const double c = (double)L.size() + 1.0;
+        flops += c * c;
+        if (flops > limit) { *aborted = true; return flops; }
+        if (parent[j] < 0) std::vector<int32_t>().swap(L);
+    }
+    return flops;
+}
+
 }  // namespace
 
 void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
@@ -47,8 +100,18 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
     } else {
         std::vector<int64_t> xadj; std::vector<int32_t> adj;
         build_sym_graph(N, colptr, rowval, xadj, adj);
-        if (opt.ordering == 0) amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
-        else nd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, p0.data());
+        amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
+        if (opt.ordering == 1) {
+            // auto: nested dissection (shallow, wide trees for the level-scheduled kernels and the
+            // multi-GPU split) unless it costs more than nd_max_cost_ratio x the AMD-class ordering
+            std::vector<int32_t> pn(N), ipa(N), ipn(N);
+            nd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, pn.data());
+            for (int32_t k = 0; k < N; ++k) { ipa[p0[k]] = k; ipn[pn[k]] = k; }
+            bool ab = false;
+            const double fa = ordering_cost(N, colptr, rowval, ipa, 1e300, &ab);
+            const double fn = ordering_cost(N, colptr, rowval, ipn, opt.nd_max_cost_ratio * fa, &ab);
+            if (!ab) p0.swap(pn);
+        }
     }
     std::vector<int32_t> ip0(N);
     for (int32_t k = 0; k < N; ++k) ip0[p0[k]] = k;

@@ -9,9 +9,11 @@
 namespace cb200 {
 
 struct SymbolicOptions {
-    int32_t ordering = 1;        // 0 = AMD, 1 = nested dissection over AMD leaves, 2 = natural
-    double dense_scale = 1.5;    // AMD dense-row threshold multiplier (reference uses 1.5)
+    int32_t ordering = 1;        // 0 = AMD, 1 = auto (nested dissection unless much costlier than AMD), 2 = natural
+    double dense_scale = 0.3;    // AMD dense-row threshold multiplier (reference: 1.5; rows above
+                                 // 10*scale*sqrt(N) are ordered last, where they end up anyway)
     int32_t nd_leaf = 96;        // ND leaf size
+    double nd_max_cost_ratio = 3.0;  // ordering 1: keep ND only if flops <= ratio * AMD flops
     int32_t relax_small = 8;     // always merge a last child when merged width <= this
     double relax_z1 = 0.50;      // allowed zero fraction for merged width <= 32
     double relax_z2 = 0.20;      // ... <= 96

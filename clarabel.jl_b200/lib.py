@@ -124,7 +124,7 @@ _SYM_ARRAYS = ["perm", "sn_first", "rows_ptr", "rows", "rel", "sn_parent", "pane
 class Symbolic:
     """Host-only symbolic analysis (no CUDA call)."""
 
-    def __init__(self, K, ordering=1, nd_leaf=96, dense_scale=1.5, perm=None):
+    def __init__(self, K, ordering=1, nd_leaf=96, dense_scale=0.3, perm=None):
         L = lib()
         cs = make_settings(ordering=ordering, nd_leaf_size=nd_leaf, amd_dense_scale=dense_scale)
         cp = np.ascontiguousarray(K.indptr, dtype=np.int64)
