@@ -44,7 +44,7 @@ template <class T> struct DevBuf {
     ~DevBuf() { free(); }
 };
 
-struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0; };
+struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0; bool many_children = false; };
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
@@ -143,6 +143,7 @@ struct cb200_handle {
     DevBuf<int64_t> d_cp; DevBuf<int32_t> d_ri; DevBuf<double> d_nz;
     DevBuf<int64_t> d_tp; DevBuf<int32_t> d_tc; DevBuf<int64_t> d_tpos;
     DevBuf<int64_t> d_amap, d_diagidx;
+    DevBuf<int32_t> d_long_rows; int32_t n_long_rows = 0;
     DevBuf<int8_t> d_dsign_perm, d_dsign_orig;
     DevBuf<int32_t> d_perm;
     // symbolic
@@ -155,6 +156,7 @@ struct cb200_handle {
     DevBuf<double> d_eps; DevBuf<unsigned long long> d_scal;   // [0] max|diag|, [1] normb, [2] norme
     DevBuf<unsigned int> d_nreg;
     std::vector<LevelPlan> plan;
+    std::vector<int32_t> h_batches;
     std::vector<int64_t> h_woff;
     bool have_diag = false;
     // fused (outer) boundary state
@@ -246,7 +248,10 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
         const Batch& b3 = pass == 0 ? P.solve[3] : P.tops;
         if (!b3.cnt) continue;
         const int32_t* bl = h->d_batches.p + b3.off;
-        k_big_asm_fwd<<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
+        if (b3.many_children)
+            k_big_asm_fwd<32><<<dim3(nblk((int64_t)b3.maxnf * 32, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
+        else
+            k_big_asm_fwd<1><<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
         if (pass == 1 && h->dist) {
             // sum the per-rank partial right-hand sides of the replicated top fronts
@@ -333,6 +338,7 @@ int build_plans(cb200_handle* h) {
             int nf = S.ns(sn) + S.nr(sn);
             b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
             b.maxnr = std::max(b.maxnr, S.nr(sn));
+            if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
             batches.push_back(sn);
             woff.push_back(large ? w : 0);
             if (large) w += (int64_t)nblk(S.ns(sn), PB) * PB * PB;   // parked diagonal blocks
@@ -363,6 +369,7 @@ int build_plans(cb200_handle* h) {
         add_batch(P.topf, top, true, P);
         add_batch(P.tops, top, false, P);
     }
+    h->h_batches = batches;
     CUDA_OK(h->d_batches.upload(batches, s)); CUDA_OK(h->d_woff.upload(woff, s));
     CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
     size_t pmax = 1;
@@ -469,6 +476,11 @@ int factor_body(cb200_handle* h, bool static_reg) {
             k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)B.maxnr * B.maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
             k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
             h->tm.nlaunch += 2;
+            for (int32_t k = 0; k < B.cnt; ++k) {
+                const int32_t sn = h->h_batches[B.off + k];
+                const int32_t nch = S.child_ptr[sn + 1] - S.child_ptr[sn];
+                if (nch > MANY_CHILDREN) { k_assemble_atomic<<<nch, 64, 0, st>>>(ds, sn, h->d_L.p, h->d_U.p); LAUNCH(h); }
+            }
             if (is_top && h->dist) {
                 // root-front assembly across GPUs: every rank holds the contributions of its own
                 // subtrees (rank 0 also the original entries); sum them over NVLink.
@@ -559,6 +571,12 @@ int residual(cb200_handle* h, const double* d_xi, double* d_e, int slot) {
             k_residual<4><<<nblk(h->N * 4, 256), 256, 0, st>>>(h->N, h->d_cp.p, h->d_ri.p, h->d_nz.p, h->d_tp.p,
                                                                h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p, d_e,
                                                                h->d_scal.p + slot);
+        if (h->n_long_rows) {
+            k_residual_long<<<h->n_long_rows, 256, 0, st>>>(h->d_long_rows.p, h->d_cp.p, h->d_ri.p, h->d_nz.p,
+                                                            h->d_tp.p, h->d_tc.p, h->d_tpos.p, d_xi, h->d_b.p,
+                                                            d_e, h->d_scal.p + slot);
+            LAUNCH(h);
+        }
         LAUNCH(h);
     }
     h->tm.end(st);
@@ -622,6 +640,13 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                     if (ri[p] < j) { int64_t q = pos[ri[p]]++; tc[q] = (int32_t)j; tpos[q] = p; }
         }
         CUDA_OK(h->d_tp.upload(tp, s)); CUDA_OK(h->d_tc.upload(tc, s)); CUDA_OK(h->d_tpos.upload(tpos, s));
+        {
+            std::vector<int32_t> longrows;
+            for (int64_t j = 0; j < N; ++j)
+                if ((cp[j + 1] - cp[j]) + (tp[j + 1] - tp[j]) > LONG_ROW) longrows.push_back((int32_t)j);
+            h->n_long_rows = (int32_t)longrows.size();
+            CUDA_OK(h->d_long_rows.upload(longrows, s));
+        }
         h->have_diag = std::all_of(diagidx.begin(), diagidx.end(), [](int64_t v) { return v >= 0; });
         if (h->have_diag) CUDA_OK(h->d_diagidx.upload(diagidx, s));
         CUDA_OK(h->d_amap.upload(S.a_map, s));

@@ -35,6 +35,7 @@ struct DevSym {                 // device copies of the Symbolic arrays
 };
 
 struct RegParams { double eps, delta; int enable; };
+constexpr int MANY_CHILDREN = 2048;   // fronts with more children are assembled by k_assemble_atomic
 
 
 // ------------------------------------------------------------------ inverted diagonal blocks
@@ -165,6 +166,7 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int d = blockIdx.x * ASM_CW + wid;
     if (d >= nf) return;
+    if (S.child_ptr[s + 1] - S.child_ptr[s] > MANY_CHILDREN) return;     // k_assemble_atomic
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
     double* dst = d < ns ? Lp + (int64_t)d * nf : Us + (int64_t)(d - ns) * nr - ns;
@@ -180,6 +182,34 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
         const int32_t* relc = S.rel + rp0;
         const double* src = Ust + S.upd_off[c] + (int64_t)j * nrc;
         for (int i = j + lane; i < nrc; i += 32) dst[relc[i]] += src[i];
+    }
+}
+
+// Fronts with thousands of (tiny) children — e.g. the factor-row front of a portfolio KKT system
+// with one child per asset: the destination-owner loop would serialise ~1e3 sources per column.
+// Here every child is scattered by its own warp with FP64 atomics into the (zeroed / scattered)
+// front.  This is the one place where the summation order is not fixed (documented in DESIGN.md);
+// it is used only above MANY_CHILDREN children.  grid (children), 64 threads.
+__global__ void __launch_bounds__(64)
+k_assemble_atomic(DevSym S, int s, double* __restrict__ Lst, double* __restrict__ Ust) {
+    const int c = S.child_list[S.child_ptr[s] + blockIdx.x];
+    if (S.active && !S.active[c]) return;
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    double* Lp = Lst + S.panel_off[s];
+    double* Us = Ust + S.upd_off[s];
+    const int64_t rp0 = S.rows_ptr[c];
+    const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
+    const int32_t* relc = S.rel + rp0;
+    const double* Uc = Ust + S.upd_off[c];
+    for (int e = threadIdx.x; e < nrc * nrc; e += 64) {
+        const int i = e % nrc, j = e / nrc;
+        if (i < j) continue;
+        const int dj = relc[j], di = relc[i];
+        double* dst = dj < ns ? Lp + (int64_t)dj * nf + di : Us + (int64_t)(dj - ns) * nr + (di - ns);
+        atomicAdd(dst, Uc[e]);
     }
 }
 
@@ -835,6 +865,9 @@ constexpr int WP = 256;        // panel width
 constexpr int BRT = 256;       // rows per CTA in the GEMV kernels
 
 // w = [y_s ; 0] + sum of children contributions (destination-owner form); grid (row tiles, cnt)
+// AL lanes cooperate on one destination row (AL = 32 for fronts with thousands of children);
+// the cross-lane sum is a fixed-order shuffle tree, so the result is deterministic.
+template <int AL>
 __global__ void __launch_bounds__(256)
 k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ y,
               double* __restrict__ uvec) {
@@ -843,14 +876,20 @@ k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ 
     const int ns = S.sn_first[s + 1] - f;
     const int64_t rp = S.rows_ptr[s];
     const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= nf) return;
-    const int32_t* cp = S.asm_colptr + S.front_ptr[s];
-    const int64_t base = S.asm_base[s];
-    double acc = i < ns ? y[f + i] : 0.0;
-    for (int e = cp[i]; e < cp[i + 1]; ++e)
-        if (!S.active || S.active[S.asm_child[base + e]]) acc += uvec[S.asm_src[base + e]];
-    if (i < ns) y[f + i] = acc; else uvec[rp + i - ns] = acc;
+    const int i = (blockIdx.x * 256 + threadIdx.x) / AL;
+    const int sub = threadIdx.x % AL;
+    double acc = 0.0;
+    if (i < nf) {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int e = cp[i] + sub; e < cp[i + 1]; e += AL)
+            if (!S.active || S.active[S.asm_child[base + e]]) acc += uvec[S.asm_src[base + e]];
+    }
+#pragma unroll
+    for (int o = AL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (i < nf && sub == 0) {
+        if (i < ns) y[f + i] += acc; else uvec[rp + i - ns] = acc;
+    }
 }
 
 // forward triangle of panel pk: x = inv-blocked solve of L11[kb:kb+wp, kb:kb+wp]; grid (cnt)
@@ -1039,6 +1078,7 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
 // K symmetric, stored as upper CSC (cp, ri, nz) plus the row-wise index of the same entries
 // (tp, tc, tpos: entries (j, c > j) of row j, value nz[tpos]).  RL lanes cooperate on one row
 // (KKT rows are short: ~5 + 5 entries; dense cone rows just loop), 256/RL rows per CTA.
+constexpr int LONG_ROW = 2048;     // rows with more entries are handled by k_residual_long (CTA per row)
 template <int RL>
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, const int64_t* __restrict__ cp, const int32_t* __restrict__ ri,
@@ -1050,13 +1090,14 @@ k_residual(int64_t N, const int64_t* __restrict__ cp, const int32_t* __restrict_
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / RL;
     double r = 0.0;
     double acc = 0.0;
-    if (row < N) {
+    const bool is_long = row < N && (cp[row + 1] - cp[row]) + (tp[row + 1] - tp[row]) > LONG_ROW;
+    if (row < N && !is_long) {
         for (int64_t p = cp[row] + sub; p < cp[row + 1]; p += RL) acc += nz[p] * x[ri[p]];
         for (int64_t p = tp[row] + sub; p < tp[row + 1]; p += RL) acc += nz[tpos[p]] * x[tc[p]];
     }
 #pragma unroll
     for (int o = RL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (row < N) {
+    if (row < N && !is_long) {
         r = b[row] - acc;
         if (sub == 0) e[row] = r;
     }
@@ -1070,6 +1111,33 @@ k_residual(int64_t N, const int64_t* __restrict__ cp, const int32_t* __restrict_
         double t = 0.0;
         for (int q = 0; q < 8; ++q) t = fmax(t, sm[q]);
         atomicMax(norm_bits, (unsigned long long)__double_as_longlong(t));
+    }
+}
+
+// dense rows (budget / linking constraints): one CTA per row, fixed-order tree reduction
+__global__ void __launch_bounds__(256)
+k_residual_long(const int32_t* __restrict__ rows, const int64_t* __restrict__ cp,
+                const int32_t* __restrict__ ri, const double* __restrict__ nz,
+                const int64_t* __restrict__ tp, const int32_t* __restrict__ tc,
+                const int64_t* __restrict__ tpos, const double* __restrict__ x,
+                const double* __restrict__ b, double* __restrict__ e,
+                unsigned long long* __restrict__ norm_bits) {
+    __shared__ double sm[8];
+    const int64_t row = rows[blockIdx.x];
+    double acc = 0.0;
+    for (int64_t p = cp[row] + threadIdx.x; p < cp[row + 1]; p += 256) acc += nz[p] * x[ri[p]];
+    for (int64_t p = tp[row] + threadIdx.x; p < tp[row + 1]; p += 256) acc += nz[tpos[p]] * x[tc[p]];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sm[q];
+        const double r = b[row] - t;
+        e[row] = r;
+        double m = fabs(r);
+        if (!(m == m)) m = __longlong_as_double(0x7ff0000000000000LL);
+        atomicMax(norm_bits, (unsigned long long)__double_as_longlong(m));
     }
 }
 
