@@ -283,25 +283,69 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
     nfac, nsol = max(1, tm["nfactor"]), max(1, tm["nsolve"])
     N, nnzL, nnzK = desc["N"], desc["nnzL"], desc["nnzK"]
+    stats = ks.ldl.stats()
+    # ---- FP64 compute calibration on this box (no FP64 figure in MEASURED_PEAKS.json): cuBLAS DGEMM
+    fp64_peak = None
+    try:
+        a_ = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+        b_ = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            torch.matmul(a_, b_)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        del a_, b_
+    except Exception:
+        pass
+    # ---- per-kernel-class timing of the factorisation (events around each launch group; graph
+    # replay is off for these two extra steps, they are not part of the timed region above)
+    ks.ldl.set_detail(True); ks.ldl.set_resident(True)
+    step(0)
+    ks.ldl.reset_timers()
+    for i in range(2):
+        step(i)
+    td = ks.ldl.timers()
+    ks.ldl.set_detail(False); ks.ldl.set_resident(False)
+    nfd = max(1, td["nfactor"])
     b_solve = 16.0 * nnzL + 48.0 * N
-    b_factor = 8.0 * (nnzK + nnzL + N)
     b_spmv = 8.0 * nnzK + 24.0 * N
     t_solve = tm["solve_ms"] / nsol * 1e-3
     t_fac = tm["factor_ms"] / nfac * 1e-3
     t_spmv = tm["spmv_ms"] / nsol * 1e-3
-    phases = dict(
-        triangular_solve=dict(ms_per_call=t_solve * 1e3, calls_per_step=nsol / args.steps,
-                              achieved_gbs=b_solve / t_solve / 1e9, bytes=b_solve),
-        factor=dict(ms_per_call=t_fac * 1e3, calls_per_step=nfac / args.steps,
-                    achieved_gbs=b_factor / t_fac / 1e9, bytes=b_factor),
-        spmv_residual=dict(ms_per_call=t_spmv * 1e3, calls_per_step=nsol / args.steps,
-                           achieved_gbs=b_spmv / max(t_spmv, 1e-12) / 1e9, bytes=b_spmv))
-    share = {k: v["ms_per_call"] * v["calls_per_step"] for k, v in phases.items()}
-    dom = max(share, key=share.get)
-    ach = phases[dom]["achieved_gbs"]
-    roofline = dict(bound="hbm", kernel=dom, achieved=ach, peak=hbm_peak, unit="GB/s",
-                    frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=phases[dom]["bytes"], phases=phases)
+    t_schur = td["schur_ms"] / nfd * 1e-3
+    kernels = dict(
+        triangular_solve_sweeps=dict(bound="hbm", ms_per_call=t_solve * 1e3, calls_per_step=nsol / args.steps,
+                                     achieved=b_solve / t_solve / 1e9, unit="GB/s", peak=hbm_peak,
+                                     algorithmic_bytes=b_solve),
+        spmv_residual=dict(bound="hbm", ms_per_call=t_spmv * 1e3, calls_per_step=nsol / args.steps,
+                           achieved=b_spmv / max(t_spmv, 1e-12) / 1e9, unit="GB/s", peak=hbm_peak,
+                           algorithmic_bytes=b_spmv),
+        factor_total=dict(bound="fp64", ms_per_call=t_fac * 1e3, calls_per_step=nfac / args.steps,
+                          achieved=stats["flops"] / t_fac / 1e12, unit="TFLOP/s", peak=fp64_peak,
+                          algorithmic_flops=stats["flops"]),
+        k_schur_large=dict(bound="fp64", ms_per_call=t_schur * 1e3, calls_per_step=1.0,
+                           achieved=(stats["schur_flops"] / t_schur / 1e12) if t_schur > 0 else None,
+                           unit="TFLOP/s", peak=fp64_peak, algorithmic_flops=stats["schur_flops"]),
+        factor_pivot_blocks=dict(ms_per_call=td["panel_ms"] / nfd), factor_small_fronts=dict(ms_per_call=td["small_ms"] / nfd),
+        factor_assembly=dict(ms_per_call=td["asm_ms"] / nfd))
+    for k in kernels.values():
+        if k.get("peak") and k.get("achieved") is not None:
+            k["frac"] = k["achieved"] / k["peak"]
+    # dominant kernel of the step: the largest (time per call x calls per step) among the measured ones
+    cand = {"triangular_solve_sweeps": t_solve * nsol / args.steps, "k_schur_large": t_schur,
+            "spmv_residual": t_spmv * nsol / args.steps}
+    dom = max(cand, key=cand.get)
+    kd = kernels[dom]
+    roofline = dict(bound=kd["bound"], kernel=dom, achieved=kd["achieved"], peak=kd["peak"], unit=kd["unit"],
+                    frac=kd.get("frac"), traffic=None,
+                    peak_source=(peak_src if kd["bound"] == "hbm" else
+                                 "on-box cuBLAS DGEMM 4096^3 (float64) - MEASURED_PEAKS.json has no FP64 figure"),
+                    note="bound 'fp64' = FP64 FMA pipe (tcgen05 has no f64 kind; see DESIGN.md section 4)",
+                    kernels=kernels)
     line = dict(metric=metric, value=args.steps / (ms_res * 1e-3), unit="it/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_res / args.steps,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",

@@ -59,21 +59,23 @@ struct LevelPlan {
 };
 
 struct Timers {
-    enum { CONE = 0, FACTOR = 1, SOLVE = 2, SPMV = 3, NPH = 4 };
-    double ms[NPH] = {0, 0, 0, 0};
+    enum { CONE = 0, FACTOR = 1, SOLVE = 2, SPMV = 3, SCHUR = 4, PANEL = 5, SMALL = 6, ASM = 7, NPH = 8 };
+    double ms[NPH] = {0, 0, 0, 0, 0, 0, 0, 0};
     double nfactor = 0, nsolve = 0, nlaunch = 0;
     std::vector<cudaEvent_t> pool;
-    struct Seg { int ph; cudaEvent_t a, b; };
+    struct Seg { int ph; cudaEvent_t a, b; bool closed; };
     std::vector<Seg> open;
     size_t used = 0;
     cudaEvent_t get() {
         if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
         return pool[used++];
     }
-    void begin(int ph, cudaStream_t st) { Seg s{ph, get(), get()}; cudaEventRecord(s.a, st); open.push_back(s); }
-    void end(cudaStream_t st) { cudaEventRecord(open.back().b, st); }
+    void begin(int ph, cudaStream_t st) { Seg s{ph, get(), get(), false}; cudaEventRecord(s.a, st); open.push_back(s); }
+    void end(cudaStream_t st) {        // closes the most recently opened, still open segment (segments nest)
+        for (size_t i = open.size(); i-- > 0;) if (!open[i].closed) { cudaEventRecord(open[i].b, st); open[i].closed = true; return; }
+    }
     void collect() {      // call after a stream synchronise
-        for (auto& s : open) { float t = 0; cudaEventElapsedTime(&t, s.a, s.b); ms[s.ph] += t; }
+        for (auto& s : open) { float t = 0; if (s.closed && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.ph] += t; }
         open.clear(); used = 0;
     }
     ~Timers() { for (auto e : pool) cudaEventDestroy(e); }
@@ -183,6 +185,7 @@ struct cb200_handle {
     DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
     double last_eps = 0;
     bool resident = false;
+    bool detail = false;       // per-kernel-class event timing (disables graph replay)
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -412,7 +415,7 @@ __global__ void k_zero_upd(DevSym S, const int32_t* batch, double* Ust) {
 // launch sequence of a factorisation / solve sweep only depends on the symbolic structure, so it
 // is captured once and relaunched with one call per IP iteration.
 template <class F> int run_captured(cb200_handle* h, GraphExec& g, F body) {
-    if (!h->st.use_cuda_graph || g.failed) return body();
+    if (!h->st.use_cuda_graph || g.failed || h->detail) return body();
     if (!g.exec) {
         const double l0 = h->tm.nlaunch;
         cudaGraph_t graph = nullptr;
@@ -461,18 +464,21 @@ int factor_body(cb200_handle* h, bool static_reg) {
     }
     for (int lv = 0; lv < S.nlevels; ++lv) {
         const LevelPlan& P = h->plan[lv];
+        if (h->detail) h->tm.begin(Timers::SMALL, st);
         launch_small<32>(h, P.small[0], 16, rp);
         launch_small<64>(h, P.small[1], 32, rp);
         launch_small<128>(h, P.small[2], 64, rp);
         launch_small<256>(h, P.small[3], 96, rp);
         launch_small<256>(h, P.small[4], 128, rp);
         launch_small<256>(h, P.small[5], 160, rp);
+        if (h->detail) h->tm.end(st);
         for (int pass = 0; pass < 2; ++pass) {
             const Batch& B = pass == 0 ? P.large : P.topf;
             if (!B.cnt) continue;
             const bool is_top = pass == 1;
             const int32_t* bl = h->d_batches.p + B.off;
             const int64_t* wo = h->d_woff.p + B.off;
+            if (h->detail) h->tm.begin(Timers::ASM, st);
             k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)B.maxnr * B.maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
             k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
             h->tm.nlaunch += 2;
@@ -488,6 +494,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                 int rc = allreduce_fronts(h, B, list);
                 if (rc) return rc;
             }
+            if (h->detail) { h->tm.end(st); h->tm.begin(Timers::PANEL, st); }
             const size_t sm64 = (size_t)(4 * GBK * GBM + 2 * PB * (PB + 1)) * sizeof(double);
             for (int kb = 0; kb < B.maxns; kb += PB) {
                 k_diag64<<<B.cnt, 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
@@ -500,6 +507,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                     LAUNCH(h);
                 }
             }
+            if (h->detail) { h->tm.end(st); h->tm.begin(Timers::SCHUR, st); }
             {
                 const int T = nblk(B.maxnr, GBM);
                 if (T > 0) {
@@ -507,6 +515,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                     LAUNCH(h);
                 }
             }
+            if (h->detail) h->tm.end(st);
             k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
@@ -1006,8 +1015,9 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len) 
 }
 
 int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len) {
-    double v[7] = {h->tm.ms[0], h->tm.ms[1], h->tm.ms[2], h->tm.ms[3], h->tm.nfactor, h->tm.nsolve, h->tm.nlaunch};
-    for (int i = 0; i < len && i < 7; ++i) out[i] = v[i];
+    double v[11] = {h->tm.ms[0], h->tm.ms[1], h->tm.ms[2], h->tm.ms[3], h->tm.nfactor, h->tm.nsolve, h->tm.nlaunch,
+                    h->tm.ms[4], h->tm.ms[5], h->tm.ms[6], h->tm.ms[7]};
+    for (int i = 0; i < len && i < 11; ++i) out[i] = v[i];
     return 0;
 }
 int32_t cb200_nccl_unique_id(char out[128]) {
@@ -1062,6 +1072,26 @@ int32_t cb200_dist_init(cb200_handle* h, int32_t rank, int32_t nranks, const cha
         CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int32_t cb200_set_detail(cb200_handle* h, int32_t on) { h->detail = on != 0; return 0; }
+
+int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
+    const Symbolic& S = h->S;
+    double schur = 0, panel_large = 0, big_bytes = 0, nlarge = 0;
+    for (int32_t sn = 0; sn < S.nsuper; ++sn) {
+        const double ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
+        if (nf > kSmallNf[NSMALL - 1]) {
+            nlarge += 1;
+            schur += nr * (nr + 1.0) * ns;                 // flops of F22 -= L21 D L21' (lower part)
+            for (double k = 0; k < ns; ++k) panel_large += (nf - k) * (nf - k);
+        }
+        if (nf * ns >= 65536 && ns > 32) big_bytes += 8.0 * nf * ns;
+    }
+    double v[10] = {S.flops, schur, panel_large - schur, (double)S.nnzL, (double)S.nlevels, (double)S.nsuper,
+                    nlarge, big_bytes, (double)S.upd_total * 8.0, (double)S.panel_off.back() * 8.0};
+    for (int i = 0; i < len && i < 10; ++i) out[i] = v[i];
+    return 0;
 }
 
 void* cb200_get_stream(cb200_handle* h) { return (void*)h->stream; }

@@ -94,10 +94,21 @@ class B200DirectLDLSolver:
         return out
 
     def timers(self):
-        out = np.zeros(7)
-        self._L.cb200_get_timers(self._h, _p(out), 7)
+        out = np.zeros(11)
+        self._L.cb200_get_timers(self._h, _p(out), 11)
         return dict(cone_ms=out[0], factor_ms=out[1], solve_ms=out[2], spmv_ms=out[3],
-                    nfactor=int(out[4]), nsolve=int(out[5]), nlaunch=int(out[6]))
+                    nfactor=int(out[4]), nsolve=int(out[5]), nlaunch=int(out[6]),
+                    schur_ms=out[7], panel_ms=out[8], small_ms=out[9], asm_ms=out[10])
+
+    def set_detail(self, on):
+        self._L.cb200_set_detail(self._h, int(bool(on)))
+
+    def stats(self):
+        out = np.zeros(10)
+        self._L.cb200_get_stats(self._h, _p(out), 10)
+        keys = ["flops", "schur_flops", "panel_flops", "nnzL", "nlevels", "nsuper", "nlarge",
+                "big_solve_bytes", "upd_bytes", "panel_bytes"]
+        return dict(zip(keys, out.tolist()))
 
     def reset_timers(self):
         self._L.cb200_reset_timers(self._h)

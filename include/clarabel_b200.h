@@ -129,9 +129,17 @@ int32_t cb200_update_A(cb200_handle* h, const double* values, int64_t len);
  *       3 perm (as doubles), 4 last static regulariser (len 1), 5 regularised-pivot count (len 1) */
 int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len);
 /* timers (ms, accumulated CUDA-event times on the handle's stream): 0 cone update + scatter,
- * 1 factor, 2 triangular solves, 3 spmv/residual ; counters: 4 #factor, 5 #solves, 6 #kernel launches */
+ * 1 factor, 2 triangular solves, 3 spmv/residual ; counters: 4 #factor, 5 #solves, 6 #kernel launches ;
+ * with cb200_set_detail(h,1) also per kernel class inside the factorisation: 7 k_schur_large,
+ * 8 pivot-block phase (k_diag64 + k_rows64), 9 small fronts (k_factor_small), 10 assembly */
 int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len);
 int32_t cb200_reset_timers(cb200_handle* h);
+/* per-kernel-class event timing inside the factorisation (disables CUDA-graph replay while on) */
+int32_t cb200_set_detail(cb200_handle* h, int32_t on);
+/* symbolic statistics: 0 factor flops (sum of squared column lengths), 1 flops of the large-front
+ * Schur GEMMs, 2 flops of the large-front panel phase, 3 nnzL, 4 levels, 5 supernodes, 6 large
+ * fronts, 7 panel bytes of the multi-CTA solve class, 8 update-storage bytes, 9 panel-storage bytes */
+int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len);
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU)
  * Every rank creates the same handle on its own device (replicated symbolic analysis), then
  * calls cb200_dist_init with a NCCL unique id obtained on rank 0 (cb200_nccl_unique_id) and
