@@ -48,7 +48,7 @@ struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0; bool m
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
-constexpr int NSOLVE = 4;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big)
+constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -235,6 +235,12 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
                                                              h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
     }
+    const Batch& b4 = P.solve[4];
+    if (b4.cnt) {
+        k_fwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
+                                                                   h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+    }
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
         k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
@@ -275,7 +281,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
             k_big_tri_fwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, h->d_L.p, h->d_y.p);
             const int rows_below = b3.maxnf - pk * WP;     // upper bound
             if (rows_below > 0) {
-                k_big_gemv_fwd<<<dim3(nblk(rows_below, BRT), b3.cnt), BRT, 0, h->stream>>>(
+                k_big_gemv_fwd<<<dim3(nblk(rows_below, BRT), b3.cnt), 256, 0, h->stream>>>(
                     ds, bl, pk, h->d_L.p, h->d_y.p, h->d_uvec.p);
                 LAUNCH(h);
             }
@@ -313,6 +319,12 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     if (b1.cnt) {
         k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
+        LAUNCH(h);
+    }
+    const Batch& b4 = P.solve[4];
+    if (b4.cnt) {
+        k_bwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
+                                                                   h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
     }
     const Batch& b0 = P.solve[0];
@@ -361,7 +373,8 @@ int build_plans(cb200_handle* h) {
             cls[c].push_back(sn);
             const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
             const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
-            const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2));
+            const bool tiny = S.ns(sn) <= SG && nf <= 32;
+            const int d = leaf ? 0 : (tiny ? 4 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2)));
             scl[d].push_back(sn);
         }
         LevelPlan& P = h->plan[lv];
@@ -414,8 +427,9 @@ __global__ void k_zero_upd(DevSym S, const int32_t* batch, double* Ust) {
 // Replays `body` (a fixed sequence of stream operations on h->stream) through a CUDA graph: the
 // launch sequence of a factorisation / solve sweep only depends on the symbolic structure, so it
 // is captured once and relaunched with one call per IP iteration.
-template <class F> int run_captured(cb200_handle* h, GraphExec& g, F body) {
-    if (!h->st.use_cuda_graph || g.failed || h->detail) return body();
+template <class F> int run_captured(cb200_handle* h, GraphExec& g, F body, int bit = 1) {
+    // use_cuda_graph is a bit mask: 1 = solve sweeps, 2 = factorisation
+    if (!(h->st.use_cuda_graph & bit) || g.failed || h->detail) return body();
     if (!g.exec) {
         const double l0 = h->tm.nlaunch;
         cudaGraph_t graph = nullptr;
@@ -495,7 +509,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
                 if (rc) return rc;
             }
             if (h->detail) { h->tm.end(st); h->tm.begin(Timers::PANEL, st); }
-            const size_t sm64 = (size_t)(4 * GBK * GBM + 2 * PB * (PB + 1)) * sizeof(double);
+            const size_t sm64 = (size_t)(GSM + 2 * PB * (PB + 1)) * sizeof(double);
             for (int kb = 0; kb < B.maxns; kb += PB) {
                 k_diag64<<<B.cnt, 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
                                                    rp, h->d_nreg.p);
@@ -526,7 +540,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
 
 int factor(cb200_handle* h, bool static_reg) {
     h->tm.begin(Timers::FACTOR, h->stream);
-    int rc = run_captured(h, h->g_factor[static_reg ? 1 : 0], [&]() { return factor_body(h, static_reg); });
+    int rc = run_captured(h, h->g_factor[static_reg ? 1 : 0], [&]() { return factor_body(h, static_reg); }, 2);
     h->tm.end(h->stream);
     h->tm.nfactor += 1;
     return rc;
@@ -698,9 +712,9 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (32 * 32 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_diag64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (4 * GBK * GBM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
+                                     (GSM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_rows64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (4 * GBK * GBM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
+                                     (GSM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); delete h; return -4; }

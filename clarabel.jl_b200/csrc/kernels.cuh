@@ -227,43 +227,58 @@ __device__ __forceinline__ double* front_col(double* Lp, double* Us, int ns, int
     return g < ns ? Lp + (int64_t)g * nf : Us + (int64_t)(g - ns) * nr - ns;
 }
 
-// acc (4 x BN/16 per thread) = sum_{k in [k0,k1)} L[rowA0 + i, k] * D[k] * L[rowB0 + j, k]
-// 256 threads, tile 64 x BN, K-step 16, register prefetch + double-buffered shared memory.
-template <int BN>
+// acc (4 x 4 per thread, rows tx*4+a, cols ty*4+c) = sum_{k in [k0,k1)} L[rowA0+i, k] D[k] L[rowB0+j, k]
+// 64 x 64 tile, 256 threads = 8 warps (2 x 4), each warp 32 x 16 of the tile as 4 x 2 FP64
+// tensor-core fragments: mma.sync.aligned.m8n8k4.f64 (DMMA - the FP64 path of the tensor cores;
+// tcgen05 has no f64 kind).  K-step 16 (4 mma k-steps), register prefetch of the next K-slab,
+// double-buffered shared memory with a 72-double row stride (conflict-free fragment loads).
+constexpr int GLD = 72;                        // smem row stride (doubles)
+constexpr int GSM = 2 * 2 * GBK * GLD;         // doubles of shared memory used by the tile routine
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int nf,
                                               const double* __restrict__ Dv, int rowA0, int rowB0,
-                                              int k0, int k1, double (&acc)[4][BN / 16],
-                                              double (*As)[GBK][GBM], double (*Bs)[GBK][BN]) {
-    constexpr int CN = BN / 16;
+                                              int k0, int k1, double (&acc)[4][4], double* gsm) {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < CN; ++c) acc[a][c] = 0.0;
-    // loader mapping: element e = tid + 256 u ; row = e % 64, k = e / 64  (A: 4 per thread)
-    double ra[4], rb[BN / 16];
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    if (k0 >= k1) return;
+    double* As = gsm;                           // [2][GBK][GLD]
+    double* Bs = gsm + 2 * GBK * GLD;           // [2][GBK][GLD]
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wm = (wid & 1) * 32, wn = (wid >> 1) * 16;     // warp origin inside the tile
+    const int g = lane >> 2, t = lane & 3;
+    double cf[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { cf[i][j][0] = 0.0; cf[i][j][1] = 0.0; }
+    // loader mapping: element e = tid + 256 u ; row = e % 64, k = e / 64  (4 of A, 4 of B per thread)
+    double ra[4], rb[4];
     auto gload = [&](int kk) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + 256 * u, r = e & 63, k = kk + (e >> 6);
-            const int gr = rowA0 + r;
-            ra[u] = (k < k1 && gr < nf) ? Lp[(int64_t)k * nf + gr] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < BN / 16; ++u) {
-            const int e = tid + 256 * u, r = e % BN, k = kk + e / BN;
-            const int gr = rowB0 + r;
-            rb[u] = (k < k1 && gr < nf) ? Lp[(int64_t)k * nf + gr] * Dv[k] : 0.0;
+            const int ga = rowA0 + r, gb = rowB0 + r;
+            ra[u] = (k < k1 && ga < nf) ? Lp[(int64_t)k * nf + ga] : 0.0;
+            rb[u] = (k < k1 && gb < nf) ? Lp[(int64_t)k * nf + gb] * Dv[k] : 0.0;
         }
     };
     auto sstore = [&](int buf) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u; As[buf][e >> 6][e & 63] = ra[u]; }
-#pragma unroll
-        for (int u = 0; u < BN / 16; ++u) { const int e = tid + 256 * u; Bs[buf][e / BN][e % BN] = rb[u]; }
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u;
+            As[(buf * GBK + (e >> 6)) * GLD + (e & 63)] = ra[u];
+            Bs[(buf * GBK + (e >> 6)) * GLD + (e & 63)] = rb[u];
+        }
     };
-    if (k0 >= k1) return;
     gload(k0);
     sstore(0);
     __syncthreads();
@@ -271,22 +286,40 @@ __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int
     for (int kk = k0; kk < k1; kk += GBK) {
         const bool more = kk + GBK < k1;
         if (more) gload(kk + GBK);
+        const double* Ab = As + buf * GBK * GLD;
+        const double* Bb = Bs + buf * GBK * GLD;
 #pragma unroll
-        for (int k = 0; k < GBK; ++k) {
-            double av[4], bv[CN];
+        for (int k4 = 0; k4 < GBK; k4 += 4) {
+            double af[4], bf[2];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = As[buf][k][tx * 4 + a];
+            for (int i = 0; i < 4; ++i) af[i] = Ab[(k4 + t) * GLD + wm + 8 * i + g];
 #pragma unroll
-            for (int c = 0; c < CN; ++c) bv[c] = Bs[buf][k][ty * CN + c];
+            for (int j = 0; j < 2; ++j) bf[j] = Bb[(k4 + t) * GLD + wn + 8 * j + g];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < CN; ++c) acc[a][c] += av[a] * bv[c];
+                for (int j = 0; j < 2; ++j) dmma884(cf[i][j][0], cf[i][j][1], af[i], bf[j]);
         }
-        if (more) { sstore(buf ^ 1); }
+        if (more) sstore(buf ^ 1);
         __syncthreads();
         buf ^= 1;
     }
+    // redistribute the fragments through shared memory to the (tx, ty) 4 x 4 ownership the callers use
+    double* Cs = gsm;                           // 64 x 65 doubles, aliases the operand buffers
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = wm + 8 * i + g, c = wn + 8 * j + 2 * t;
+            Cs[r * 65 + c] = cf[i][j][0];
+            Cs[r * 65 + c + 1] = cf[i][j][1];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = Cs[(tx * 4 + a) * 65 + ty * 4 + c];
+    __syncthreads();
 }
 
 // Pivot block J (PB = 64 columns) of the large fronts of a level, two launches:
@@ -302,9 +335,8 @@ k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __re
          double* __restrict__ Wst, const int64_t* __restrict__ woff, double* __restrict__ D,
          double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
     extern __shared__ double smem[];
-    double (*As)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem);
-    double (*Bs)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem + 2 * GBK * GBM);
-    double* A = smem + 4 * GBK * GBM;                 // 64 x 65
+    double* gsm = smem;
+    double* A = smem + GSM;                           // 64 x 65
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -314,7 +346,7 @@ k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __re
     const double* Lp = Lst + S.panel_off[s];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double acc[4][4];
-    ldl_gemm_tile<GBM>(Lp, nf, D + f, J0, J0, 0, J0, acc, As, Bs);
+    ldl_gemm_tile(Lp, nf, D + f, J0, J0, 0, J0, acc, gsm);
     if (J0 == 0) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -384,9 +416,8 @@ k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict
          const double* __restrict__ Wst, const int64_t* __restrict__ woff,
          const double* __restrict__ D, const double* __restrict__ Dinv) {
     extern __shared__ double smem[];
-    double (*As)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem);
-    double (*Bs)[GBK][GBM] = reinterpret_cast<double (*)[GBK][GBM]>(smem + 2 * GBK * GBM);
-    double* Ts = smem + 4 * GBK * GBM;                // T: 64 rows x 65 (k index fastest -> [i][k])
+    double* gsm = smem;
+    double* Ts = smem + GSM;                          // T: 64 rows x 65 (k index fastest -> [i][k])
     double* Ms = Ts + PB * (PB + 1);                  // M[k][j], 64 x 65
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
@@ -399,7 +430,7 @@ k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict
     double* Lp = Lst + S.panel_off[s];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double acc[4][4];
-    ldl_gemm_tile<GBM>(Lp, nf, D + f, r0, J0, 0, J0, acc, As, Bs);
+    ldl_gemm_tile(Lp, nf, D + f, r0, J0, 0, J0, acc, gsm);
     if (J0 == 0) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -460,8 +491,7 @@ k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict
 __global__ void __launch_bounds__(256)
 k_schur_large(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
               double* __restrict__ Ust, const double* __restrict__ D) {
-    __shared__ double As[2][GBK][GBM];
-    __shared__ double Bs[2][GBK][GBM];
+    __shared__ double gsm[GSM];
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -476,7 +506,7 @@ k_schur_large(DevSym S, const int32_t* __restrict__ batch, const double* __restr
     const int tj = idx - ti * (ti + 1) / 2;
     const double* Lp = Lst + S.panel_off[s];
     double acc[4][4];
-    ldl_gemm_tile<GBM>(Lp, nf, D + f, ns + ti * GBM, ns + tj * GBM, 0, ns, acc, As, Bs);
+    ldl_gemm_tile(Lp, nf, D + f, ns + ti * GBM, ns + tj * GBM, 0, ns, acc, gsm);
     double* Us = Ust + S.upd_off[s];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
@@ -748,6 +778,85 @@ k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     if (lane < ns) y[f + lane] = xj;
 }
 
+// --- tiny supernodes (ns <= 8, nf <= 32, with children): 8 lanes per supernode, 32 supernodes
+// per CTA.  Groups of one warp diverge freely: every shuffle / sync uses the group's own mask.
+constexpr int SG = 8;
+__global__ void __launch_bounds__(256)
+k_fwd_sub(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
+          double* __restrict__ y, double* __restrict__ uvec) {
+    __shared__ double smem[256 / SG][32];
+    const int g = threadIdx.x / SG, sub = threadIdx.x % SG;
+    const int idx = blockIdx.x * (256 / SG) + g;
+    if (idx >= count) return;
+    const unsigned mask = ((1u << SG) - 1u) << (((threadIdx.x & 31) / SG) * SG);
+    double* w = smem[g];
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const int nf = ns + nr;
+    {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int i = sub; i < nf; i += SG) {
+            double acc = i < ns ? y[f + i] : 0.0;
+            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+            w[i] = acc;
+        }
+    }
+    __syncwarp(mask);
+    const double* Lp = Lst + S.panel_off[s];
+    double xi = 0.0;
+    if (sub < ns) {
+        xi = w[sub];
+        for (int j = 0; j < sub; ++j) xi += Lp[(int64_t)j * nf + sub] * w[j];
+    }
+    __syncwarp(mask);
+    if (sub < ns) { w[sub] = xi; y[f + sub] = xi; }
+    __syncwarp(mask);
+    for (int r = ns + sub; r < nf; r += SG) {
+        double acc = w[r];
+        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * nf + r] * w[j];
+        uvec[rp + r - ns] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bwd_sub(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
+          const double* __restrict__ Dinv, double* __restrict__ y) {
+    __shared__ double smem[256 / SG][32];
+    const int g = threadIdx.x / SG, sub = threadIdx.x % SG;
+    const int idx = blockIdx.x * (256 / SG) + g;
+    if (idx >= count) return;
+    const int gbase = ((threadIdx.x & 31) / SG) * SG;
+    const unsigned mask = ((1u << SG) - 1u) << gbase;
+    double* w = smem[g];
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const int nf = ns + nr;
+    for (int i = sub; i < nf; i += SG) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
+    __syncwarp(mask);
+    const double* Lp = Lst + S.panel_off[s];
+    double tj = 0.0;
+    for (int j = 0; j < ns; ++j) {
+        const double* cj = Lp + (int64_t)j * nf;
+        double acc = 0.0;
+        for (int r = ns + sub; r < nf; r += SG) acc += cj[r] * w[r];
+        for (int o = SG / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(mask, acc, o);
+        if (sub == j) tj = w[j] - acc;
+    }
+    double xj = tj;
+    for (int i = 1; i < ns; ++i) {
+        const double ti = __shfl_sync(mask, tj, gbase + i);
+        if (sub < i) xj += Lp[(int64_t)sub * nf + i] * ti;
+    }
+    if (sub < ns) y[f + sub] = xj;
+}
+
 // --- wide supernodes: one CTA (256 threads) per supernode, blocked over SB pivot columns
 __global__ void __launch_bounds__(256)
 k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
@@ -862,7 +971,7 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
 // over all rows below the panel.  The work vector lives in place: top part in y[f..f+ns), bottom
 // part in uvec[rows_ptr[s]..).  Panels run as separate launches (stream order = dependency).
 constexpr int WP = 256;        // panel width
-constexpr int BRT = 256;       // rows per CTA in the GEMV kernels
+constexpr int BRT = 64;        // rows per CTA in the GEMV kernels
 
 // w = [y_s ; 0] + sum of children contributions (destination-owner form); grid (row tiles, cnt)
 // AL lanes cooperate on one destination row (AL = 32 for fronts with thousands of children);
@@ -930,11 +1039,14 @@ k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double*
     if (tid < wp) y[f + kb0 + tid] = w[tid];
 }
 
-// forward GEMV below panel pk: w[r] -= sum_j L[r, kb0+j] x_j ; grid (row tiles, cnt)
-__global__ void __launch_bounds__(BRT)
+// forward GEMV below panel pk: w[r] -= sum_j L[r, kb0+j] x_j ; grid (row tiles of BRT rows, cnt).
+// 256 threads = 64 rows x 4 column quarters: short dependent chains, many CTAs even when a level
+// holds a single big front.
+__global__ void __launch_bounds__(256)
 k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double* __restrict__ Lst,
                double* __restrict__ y, double* __restrict__ uvec) {
     __shared__ double xs[WP];
+    __shared__ double red[4][BRT];
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -946,26 +1058,35 @@ k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double
     const int r0 = kb0 + wp + blockIdx.x * BRT;
     if (r0 >= nf) return;
     const int tid = threadIdx.x;
-    for (int j = tid; j < wp; j += BRT) xs[j] = y[f + kb0 + j];
+    for (int j = tid; j < wp; j += 256) xs[j] = y[f + kb0 + j];
     __syncthreads();
-    const int r = r0 + tid;
-    if (r >= nf) return;
-    const double* rowp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int j = 0;
-    for (; j + 16 <= wp; j += 16) {
-        double v[16];
+    const int rl = tid & (BRT - 1), q = tid / BRT;          // row in tile, column quarter
+    const int r = r0 + rl;
+    double acc = 0.0;
+    if (r < nf) {
+        const double* rowp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r;
+        const int j0 = q * (WP / 4), j1 = min(wp, j0 + WP / 4);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = j0;
+        for (; j + 16 <= j1; j += 16) {
+            double v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * nf];
+            for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * nf];
 #pragma unroll
-        for (int u = 0; u < 16; u += 4) {
-            a0 += v[u] * xs[j + u]; a1 += v[u + 1] * xs[j + u + 1];
-            a2 += v[u + 2] * xs[j + u + 2]; a3 += v[u + 3] * xs[j + u + 3];
+            for (int u = 0; u < 16; u += 4) {
+                a0 += v[u] * xs[j + u]; a1 += v[u + 1] * xs[j + u + 1];
+                a2 += v[u + 2] * xs[j + u + 2]; a3 += v[u + 3] * xs[j + u + 3];
+            }
         }
+        for (; j < j1; ++j) a0 += rowp[(int64_t)j * nf] * xs[j];
+        acc = (a0 + a1) + (a2 + a3);
     }
-    for (; j < wp; ++j) a0 += rowp[(int64_t)j * nf] * xs[j];
-    const double acc = (a0 + a1) + (a2 + a3);
-    if (r < ns) y[f + r] -= acc; else uvec[rp + r - ns] -= acc;
+    red[q][rl] = acc;
+    __syncthreads();
+    if (q == 0 && r < nf) {
+        const double t = (red[0][rl] + red[1][rl]) + (red[2][rl] + red[3][rl]);
+        if (r < ns) y[f + r] -= t; else uvec[rp + r - ns] -= t;
+    }
 }
 
 // backward, transposed GEMV below panel pk: partial[tile][j] = sum_{r in tile} L[r, kb0+j] w_r

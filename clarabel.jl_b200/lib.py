@@ -115,6 +115,8 @@ def make_settings(settings=None, **over):
                   "iterative_refinement_abstol", "iterative_refinement_max_iter",
                   "iterative_refinement_stop_ratio"):
             setattr(cs, f, type(getattr(cs, f))(getattr(settings, f)))
+    if os.environ.get("CB200_GRAPH") is not None:     # bit mask: 1 solve sweeps, 2 factorisation
+        cs.use_cuda_graph = int(os.environ["CB200_GRAPH"])
     for k, v in over.items():
         setattr(cs, k, v)
     return cs

@@ -46,7 +46,7 @@ typedef struct cb200_settings {
     int32_t ordering;                   /* 0 AMD, 1 auto: nested dissection unless > 3x AMD cost (default), 2 natural */
     double  amd_dense_scale;            /* dense-row threshold multiplier (reference QDLDL path: 1.5, directldl_qdldl.jl:24; default here 0.3) */
     int32_t nd_leaf_size;
-    int32_t use_cuda_graph;             /* capture factor / solve launch sequences */
+    int32_t use_cuda_graph;             /* bit mask: 1 replay the solve sweeps, 2 the factorisation, through CUDA graphs */
     int32_t reserved[8];
 } cb200_settings;
 
