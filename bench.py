@@ -171,7 +171,14 @@ class FakeOracleCones:
         return cones
 
 
+def _watchdog(seconds):
+    """A hung collective must not hang the caller: dump stacks and exit non-zero."""
+    import faulthandler
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def main():
+    _watchdog(int(os.environ.get("CB200_BENCH_TIMEOUT", "840")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -271,7 +278,22 @@ def main():
     tm = ks.ldl.timers()
     stop.set(); th.join(timeout=2)
     ks.ldl.set_resident(False)
+    # ---- per-kernel-class timing of the factorisation (events around each launch group; graph
+    # replay is off for these extra steps, they are not part of the timed regions above).  In
+    # multi-GPU mode EVERY rank must execute them (they contain collectives).
+    ks.ldl.set_detail(True); ks.ldl.set_resident(True)
+    step(0)
+    ks.ldl.reset_timers()
+    for i in range(2):
+        step(i)
+    td = ks.ldl.timers()
+    ks.ldl.set_detail(False); ks.ldl.set_resident(False)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     desc = describe(name, P, A, ks)
     peaks = {}
@@ -301,15 +323,6 @@ def main():
         del a_, b_
     except Exception:
         pass
-    # ---- per-kernel-class timing of the factorisation (events around each launch group; graph
-    # replay is off for these two extra steps, they are not part of the timed region above)
-    ks.ldl.set_detail(True); ks.ldl.set_resident(True)
-    step(0)
-    ks.ldl.reset_timers()
-    for i in range(2):
-        step(i)
-    td = ks.ldl.timers()
-    ks.ldl.set_detail(False); ks.ldl.set_resident(False)
     nfd = max(1, td["nfactor"])
     b_solve = 16.0 * nnzL + 48.0 * N
     b_spmv = 8.0 * nnzK + 24.0 * N
@@ -360,6 +373,9 @@ def main():
         line["cpu_baseline"] = dict(value=v, unit="it/s", cores=1, kind="port", sample=note,
                                     sample_config=sdesc, ms_per_step=ms)
     print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
