@@ -760,6 +760,11 @@ static int finish_factor(cb200_handle* h) {
     // success = all(isfinite, Dinv)   (directldl_qdldl.jl:79)
     CUDA_OK(cudaMemsetAsync(h->d_scal.p + 3, 0, sizeof(unsigned long long), h->stream));
     if (h->N) { k_absmax<<<std::min(nblk(h->N, 256), 1184), 256, 0, h->stream>>>(h->d_Dinv.p, h->N, h->d_scal.p + 3); LAUNCH(h); }
+    if (h->dist) {
+        // every rank must take the same success / failure branch: reduce the status over the ranks
+        // (the value is the bit pattern of a non-negative double, so unsigned max == double max)
+        NCCL_OK(g_nccl.AllReduce(h->d_scal.p + 3, h->d_scal.p + 3, 1, ncclUint64, ncclMax, h->comm, h->stream));
+    }
     double v[1];
     int rc = read_scalars(h, v, 3, 1);
     if (rc) return rc;
