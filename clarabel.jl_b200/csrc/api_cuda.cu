@@ -639,7 +639,9 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         h->nnzK = nnz;
         ri.resize(nnz);
         for (int64_t i = 0; i < nnz; ++i) ri[i] = rowval[i] - base;
+        if (!g_block_hint.empty() && (int64_t)g_block_hint.size() != N) g_block_hint.clear();
         symbolic_analyze(N, cp.data(), ri.data(), options_from_settings(&st), nullptr, h->S);
+        g_block_hint.clear();
         const Symbolic& S = h->S;
         CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         cudaStream_t s = h->stream;

@@ -11,8 +11,10 @@ struct cb200_symbolic { cb200::Symbolic S; };
 namespace cb200 {
 thread_local std::string g_last_error;
 void set_error(const std::string& s) { g_last_error = s; }
+thread_local std::vector<int32_t> g_block_hint;     // consumed by the next symbolic analysis
 SymbolicOptions options_from_settings(const cb200_settings* st) {
     SymbolicOptions o;
+    o.block_id = g_block_hint.empty() ? nullptr : g_block_hint.data();
     if (st) {
         o.ordering = st->ordering;
         if (st->amd_dense_scale > 0) o.dense_scale = st->amd_dense_scale;
@@ -50,6 +52,12 @@ void cb200_default_settings(cb200_settings* s) {
     s->use_cuda_graph = 1;
 }
 
+int32_t cb200_hint_blocks(const int64_t* block_id, int64_t N) {
+    cb200::g_block_hint.clear();
+    if (block_id) { cb200::g_block_hint.resize(N); for (int64_t i = 0; i < N; ++i) cb200::g_block_hint[i] = (int32_t)block_id[i]; }
+    return 0;
+}
+
 int32_t cb200_symbolic_create(int64_t N, const int64_t* colptr, const int64_t* rowval,
                               const cb200_settings* st, const int64_t* user_perm,
                               cb200_symbolic** out) {
@@ -64,7 +72,9 @@ int32_t cb200_symbolic_create(int64_t N, const int64_t* colptr, const int64_t* r
         std::vector<int64_t> up;
         if (user_perm && base) { up.resize(N); for (int64_t i = 0; i < N; ++i) up[i] = user_perm[i] - base; user_perm = up.data(); }
         auto* s = new cb200_symbolic();
+        if (!cb200::g_block_hint.empty() && (int64_t)cb200::g_block_hint.size() != N) cb200::g_block_hint.clear();
         cb200::symbolic_analyze(N, colptr, rowval, cb200::options_from_settings(st), user_perm, s->S);
+        cb200::g_block_hint.clear();
         *out = s;
         return 0;
     } catch (const std::exception& e) { cb200::set_error(e.what()); return -1; }

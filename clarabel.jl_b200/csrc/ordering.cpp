@@ -293,8 +293,14 @@ void amd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double 
 namespace {
 
 struct NDCtx {
-    int32_t n;
+    int32_t n;                                  // vertices of the (possibly compressed) graph
     const int64_t* xadj; const int32_t* adj;
+    // clique blocks: vertex v of this graph stands for the original vertices mem[mem_ptr[v]..) and
+    // weighs wt[v]; without blocks the graph is the original one (compressed == false)
+    bool compressed = false;
+    std::vector<int32_t> wt, mem_ptr, mem, comp_of;
+    const int64_t* oxadj = nullptr; const int32_t* oadj = nullptr; int32_t on = 0;
+    std::vector<int32_t> olocal;
     std::vector<int32_t> label;      // current piece id of each vertex (-1 = already ordered)
     std::vector<int64_t> level;
     std::vector<int32_t> local;
@@ -318,11 +324,37 @@ struct NDCtx {
         return (int32_t)(maxl - stamp_base + 1);
     }
 
+    int64_t weight_of(const std::vector<int32_t>& verts) const {
+        if (!compressed) return (int64_t)verts.size();
+        int64_t w = 0; for (int32_t v : verts) w += wt[v];
+        return w;
+    }
+
     void amd_leaf(const std::vector<int32_t>& verts) {
+        int32_t lab = label[verts[0]];
+        if (compressed) {
+            // expand to original vertices and order the induced original subgraph
+            std::vector<int32_t> ov;
+            for (int32_t v : verts) for (int32_t q = mem_ptr[v]; q < mem_ptr[v + 1]; ++q) ov.push_back(mem[q]);
+            const int32_t k = (int32_t)ov.size();
+            if (k <= 2) { for (int32_t v : ov) order.push_back(v); for (int32_t v : verts) label[v] = -1; return; }
+            for (int32_t i = 0; i < k; ++i) olocal[ov[i]] = i;
+            std::vector<int64_t> lx(k + 1, 0); std::vector<int32_t> la;
+            for (int32_t i = 0; i < k; ++i) {
+                const int32_t v = ov[i];
+                for (int64_t p = oxadj[v]; p < oxadj[v + 1]; ++p)
+                    if (label[comp_of[oadj[p]]] == lab) la.push_back(olocal[oadj[p]]);
+                lx[i + 1] = (int64_t)la.size();
+            }
+            std::vector<int32_t> lp(k);
+            cb200::amd_order_graph(k, lx.data(), la.data(), dense_scale, lp.data());
+            for (int32_t i = 0; i < k; ++i) order.push_back(ov[lp[i]]);
+            for (int32_t v : verts) label[v] = -1;
+            return;
+        }
         int32_t k = (int32_t)verts.size();
         if (k <= 2) { for (int32_t v : verts) { order.push_back(v); label[v] = -1; } return; }
         for (int32_t i = 0; i < k; ++i) local[verts[i]] = i;
-        int32_t lab = label[verts[0]];
         std::vector<int64_t> lx(k + 1, 0); std::vector<int32_t> la;
         for (int32_t i = 0; i < k; ++i) {
             int32_t v = verts[i];
@@ -336,11 +368,17 @@ struct NDCtx {
         for (int32_t v : verts) label[v] = -1;
     }
 
+    void emit_vertex(int32_t v) {               // separator vertex -> its original members
+        if (compressed) for (int32_t q = mem_ptr[v]; q < mem_ptr[v + 1]; ++q) order.push_back(mem[q]);
+        else order.push_back(v);
+        label[v] = -1;
+    }
+
     int64_t stamp = 0;     // level stamps grow monotonically so level[] never needs clearing
 
     void dissect(std::vector<int32_t>& verts) {
         // verts all carry the same label
-        if ((int32_t)verts.size() <= leaf_size) { amd_leaf(verts); return; }
+        if (weight_of(verts) <= leaf_size || verts.size() == 1) { amd_leaf(verts); return; }
         int32_t lab = label[verts[0]];
         // ---- connected components (each handled independently: no separator needed)
         std::vector<int32_t> q;
@@ -358,9 +396,9 @@ struct NDCtx {
                 // small components are batched together into one AMD leaf to limit overhead
                 std::vector<int32_t> small;
                 for (auto& c : comps) {
-                    if ((int32_t)c.size() <= leaf_size) {
+                    if (weight_of(c) <= leaf_size) {
                         small.insert(small.end(), c.begin(), c.end());
-                        if ((int32_t)small.size() > leaf_size) {
+                        if (weight_of(small) > leaf_size) {
                             int32_t nl = next_label++;
                             for (int32_t v : small) label[v] = nl;
                             amd_leaf(small); small.clear();
@@ -401,8 +439,9 @@ struct NDCtx {
         if (nlev < 5) { amd_leaf(verts); return; }
         // ---- choose the smallest level in the middle half (by cumulative vertex count)
         std::vector<int64_t> lsize(nlev, 0);
-        for (int32_t v : q) lsize[level[v] - base]++;
-        int64_t tot = (int64_t)q.size(), cum = 0;
+        int64_t tot = 0;
+        for (int32_t v : q) { const int64_t w = compressed ? wt[v] : 1; lsize[level[v] - base] += w; tot += w; }
+        int64_t cum = 0;
         int32_t best = -1; double bestscore = 1e300;
         for (int32_t l = 0; l < nlev; ++l) {
             int64_t before = cum; cum += lsize[l];
@@ -436,7 +475,7 @@ struct NDCtx {
         for (int32_t v : Sp) label[v] = -2;            // taken out of both halves
         dissect(A);
         dissect(B);
-        for (int32_t v : Sp) { order.push_back(v); label[v] = -1; }
+        for (int32_t v : Sp) emit_vertex(v);
     }
 };
 
@@ -444,23 +483,71 @@ struct NDCtx {
 
 void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
                     int32_t leaf_size, int32_t* perm_out) {
+    nd_order_graph_blocks(n, xadj, adj, dense_scale, leaf_size, nullptr, perm_out);
+}
+
+// block_id (optional, length n): vertices sharing a block id >= 0 form a dense clique (a PSD or
+// dense SOC cone block of the KKT matrix) that no separator may cut: they are contracted to one
+// weighted vertex for the dissection and expanded again for the leaf orderings.
+void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out) {
     if (n == 0) return;
-    NDCtx C; C.n = n; C.xadj = xadj; C.adj = adj; C.leaf_size = std::max(8, leaf_size);
-    C.dense_scale = dense_scale;
-    C.label.assign(n, 0); C.level.assign(n, -1); C.local.assign(n, 0);
+    NDCtx C; C.leaf_size = std::max(8, leaf_size); C.dense_scale = dense_scale;
+    std::vector<int64_t> cx; std::vector<int32_t> ca;
+    bool any_block = false;
+    if (block_id) for (int32_t i = 0; i < n && !any_block; ++i) any_block = block_id[i] >= 0;
+    if (any_block) {
+        C.compressed = true; C.oxadj = xadj; C.oadj = adj; C.on = n;
+        C.comp_of.assign(n, -1); C.olocal.assign(n, 0);
+        int32_t maxb = -1;
+        for (int32_t i = 0; i < n; ++i) maxb = std::max(maxb, block_id[i]);
+        std::vector<int32_t> block_comp(maxb + 1, -1);
+        int32_t nc = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            const int32_t bid = block_id[i];
+            if (bid >= 0) { if (block_comp[bid] < 0) block_comp[bid] = nc++; C.comp_of[i] = block_comp[bid]; }
+            else C.comp_of[i] = nc++;
+        }
+        C.wt.assign(nc, 0); C.mem_ptr.assign(nc + 1, 0);
+        for (int32_t i = 0; i < n; ++i) { C.wt[C.comp_of[i]]++; C.mem_ptr[C.comp_of[i] + 1]++; }
+        for (int32_t c = 0; c < nc; ++c) C.mem_ptr[c + 1] += C.mem_ptr[c];
+        C.mem.resize(n);
+        { std::vector<int32_t> pos(C.mem_ptr.begin(), C.mem_ptr.end() - 1);
+          for (int32_t i = 0; i < n; ++i) C.mem[pos[C.comp_of[i]]++] = i; }
+        // compressed adjacency (deduplicated with a marker)
+        cx.assign(nc + 1, 0);
+        std::vector<int32_t> mark(nc, -1);
+        for (int32_t c = 0; c < nc; ++c) {
+            mark[c] = c;
+            for (int32_t q = C.mem_ptr[c]; q < C.mem_ptr[c + 1]; ++q) {
+                const int32_t v = C.mem[q];
+                for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                    const int32_t cu = C.comp_of[adj[p]];
+                    if (mark[cu] != c) { mark[cu] = c; ca.push_back(cu); }
+                }
+            }
+            cx[c + 1] = (int64_t)ca.size();
+        }
+        C.n = nc; C.xadj = cx.data(); C.adj = ca.data();
+    } else {
+        C.n = n; C.xadj = xadj; C.adj = adj;
+    }
+    const int32_t gn = C.n;
+    C.label.assign(gn, 0); C.level.assign(gn, -1); C.local.assign(gn, 0);
     C.order.reserve(n);
     double dthr = dense_scale * 10.0 * std::sqrt((double)n);
     int64_t dense = (int64_t)std::max(16.0, std::min(dthr, (double)n));
     std::vector<int32_t> dense_nodes, verts;
-    for (int32_t i = 0; i < n; ++i) {
-        if (xadj[i + 1] - xadj[i] > dense) { dense_nodes.push_back(i); C.label[i] = -1; }
+    for (int32_t i = 0; i < gn; ++i) {
+        const bool is_block = C.compressed && C.wt[i] > 1;
+        if (!is_block && C.xadj[i + 1] - C.xadj[i] > dense) { dense_nodes.push_back(i); C.label[i] = -1; }
         else verts.push_back(i);
     }
     if (!verts.empty()) C.dissect(verts);
     std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int32_t a, int32_t b) {
-        int64_t da = xadj[a + 1] - xadj[a], db = xadj[b + 1] - xadj[b];
+        int64_t da = C.xadj[a + 1] - C.xadj[a], db = C.xadj[b + 1] - C.xadj[b];
         return da < db || (da == db && a < b); });
-    for (int32_t v : dense_nodes) C.order.push_back(v);
+    for (int32_t v : dense_nodes) C.emit_vertex(v);
     for (int32_t k = 0; k < n; ++k) perm_out[k] = C.order[k];
 }
 

@@ -10,6 +10,8 @@ void amd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double 
                      int32_t* perm_out);
 void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
                     int32_t leaf_size, int32_t* perm_out);
+void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out);
 }  // namespace cb200
 
 extern "C" {

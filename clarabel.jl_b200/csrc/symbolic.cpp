@@ -105,7 +105,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             // auto: nested dissection (shallow, wide trees for the level-scheduled kernels and the
             // multi-GPU split) unless it costs more than nd_max_cost_ratio x the AMD-class ordering
             std::vector<int32_t> pn(N), ipa(N), ipn(N);
-            nd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, pn.data());
+            nd_order_graph_blocks(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, opt.block_id, pn.data());
             for (int32_t k = 0; k < N; ++k) { ipa[p0[k]] = k; ipn[pn[k]] = k; }
             bool ab = false;
             const double fa = ordering_cost(N, colptr, rowval, ipa, 1e300, &ab);

@@ -19,6 +19,8 @@ struct SymbolicOptions {
     double relax_z2 = 0.20;      // ... <= 96
     double relax_z3 = 0.05;      // otherwise
     int32_t max_width = 512;     // never merge beyond this many pivot columns
+    const int32_t* block_id = nullptr;   // optional [N]: rows sharing an id >= 0 form a dense cone block
+                                         // (clique) that nested dissection must not cut
 };
 
 struct Symbolic {

@@ -22,7 +22,7 @@ EXPORTED = [
     "cb200_download", "cb200_get_timers", "cb200_reset_timers", "cb200_last_error",
     "cb200_get_stream", "cb200_set_resident",
     "cb200_symbolic_partition", "cb200_nccl_unique_id", "cb200_dist_init",
-    "cb200_set_detail", "cb200_get_stats",
+    "cb200_set_detail", "cb200_get_stats", "cb200_hint_blocks",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
         L.cb200_dist_init.argtypes = [P, I32, I32, P]; L.cb200_dist_init.restype = I32
         L.cb200_set_detail.argtypes = [P, I32]; L.cb200_set_detail.restype = I32
         L.cb200_get_stats.argtypes = [P, P, I32]; L.cb200_get_stats.restype = I32
+        L.cb200_hint_blocks.argtypes = [P, I64]; L.cb200_hint_blocks.restype = I32
         _LIB = L
     return _LIB
 
@@ -122,6 +123,26 @@ def make_settings(settings=None, **over):
     return cs
 
 
+def hint_blocks(block_id):
+    """cb200_hint_blocks: dense cone blocks nested dissection must keep whole (None clears)."""
+    if block_id is None:
+        lib().cb200_hint_blocks(None, 0)
+    else:
+        b = np.ascontiguousarray(block_id, dtype=np.int64)
+        lib().cb200_hint_blocks(_p(b), len(b))
+
+
+def cone_block_ids(cones, n, N):
+    """block id per KKT row/column for the dense (non-diagonal) cone blocks, -1 elsewhere."""
+    bid = np.full(N, -1, dtype=np.int64)
+    k = 0
+    for i in range(len(cones.specs)):
+        if not cones.Hs_is_diagonal[i] and cones.numels[i] > 1:
+            bid[n + cones.rng_cones[i]:n + cones.rng_cones[i + 1]] = k
+            k += 1
+    return bid if k else None
+
+
 _SYM_ARRAYS = ["perm", "sn_first", "rows_ptr", "rows", "rel", "sn_parent", "panel_off", "upd_off",
                "a_map", "sn_level", "child_ptr", "child_list"]
 
@@ -129,8 +150,9 @@ _SYM_ARRAYS = ["perm", "sn_first", "rows_ptr", "rows", "rel", "sn_parent", "pane
 class Symbolic:
     """Host-only symbolic analysis (no CUDA call)."""
 
-    def __init__(self, K, ordering=1, nd_leaf=96, dense_scale=0.3, perm=None):
+    def __init__(self, K, ordering=1, nd_leaf=96, dense_scale=0.3, perm=None, block_id=None):
         L = lib()
+        hint_blocks(block_id)
         cs = make_settings(ordering=ordering, nd_leaf_size=nd_leaf, amd_dense_scale=dense_scale)
         cp = np.ascontiguousarray(K.indptr, dtype=np.int64)
         ri = np.ascontiguousarray(K.indices, dtype=np.int64)

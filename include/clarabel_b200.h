@@ -75,6 +75,12 @@ int32_t cb200_symbolic_get(const cb200_symbolic* s, int32_t which, int64_t* out,
 int32_t cb200_symbolic_partition(const cb200_symbolic* s, int32_t nranks, int64_t* owner,
                                  int64_t* is_top, double* rank_load);
 
+/* Optional ordering hint, consumed by the NEXT cb200_symbolic_create / cb200_create on this thread:
+ * block_id[i] >= 0 marks row/column i of K as part of a dense cone block (PSD triangle, dense SOC);
+ * nested dissection then keeps each block in one piece (a separator cutting such a clique was
+ * observed to destabilise the factorisation late in the IP iteration).  NULL clears the hint. */
+int32_t cb200_hint_blocks(const int64_t* block_id, int64_t N);
+
 /* Fill-reducing orderings (perm[k] = original index of the k-th pivot). */
 int32_t cb200_order_amd(int64_t n, const int64_t* colptr, const int64_t* rowval,
                         double dense_scale, int64_t* perm);

@@ -1,3 +1,5 @@
+"""CPU check of orderings on a late-iteration SDP KKT matrix: AMD vs ND vs ND with cone blocks kept
+whole, through the numpy multifrontal emulation and the QDLDL oracle (same permutation)."""
 import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np
 import clarabel_jl_b200 as cb
@@ -7,18 +9,23 @@ from oracle import qdldl as oq
 cb.register_kktsolver("qdldl", OracleDirectLDLKKTSolver)
 from common import small_instances
 from mf_numpy import MFNumpy
-P,q,A,b,K = small_instances(cb)["C4m"]()
-s = cb.Solver(P,q,A,b,K,cb.Settings(direct_solve_method="qdldl")); s.solve(max_iter=10)
+name = sys.argv[1] if len(sys.argv) > 1 else "C4m"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+P,q,A,b,K = small_instances(cb)[name]()
+s = cb.Solver(P,q,A,b,K,cb.Settings(direct_solve_method="qdldl")); s.solve(max_iter=iters)
 ks = s.kktsystem.kktsolver
-# redo the last update manually to capture shifted matrix
 s.cones.update_scaling(s.variables.s, s.variables.z, s.info.mu)
 ks.update(s.cones)
 Kd = ks.KKT.copy()
 eps = ks.diagonal_regularizer
 Kd.data[ks.map.diag_full] += np.where(ks.Dsigns==1, eps, -eps)
-print("eps", eps, "qdldl nreg", ks.ldl.regularize_count, "diag range", np.abs(Kd.data[ks.map.diag_full]).min(), np.abs(Kd.data[ks.map.diag_full]).max())
-for ordn in (0,1):
-    S = lib.Symbolic(Kd, ordering=ordn, nd_leaf=96)
-    mf = MFNumpy(S.arrays()); D = mf.factor(Kd.data, ks.Dsigns)
-    print("ordering", ordn, "MFNumpy nreg", mf.nreg, "min|D|", np.abs(D).min(), S.stats["max_front"])
-    F = oq.QDLDLFactorisation(Kd, ks.Dsigns, perm=S.arrays()["perm"]); F.refactor(); print("   qdldl w/ same perm nreg", F.regularize_count)
+N = Kd.shape[0]
+bid = lib.cone_block_ids(s.cones, s.data.n, N)
+print("eps", eps, "qdldl(AMD 1.5) nreg", ks.ldl.regularize_count, "blocks", None if bid is None else int(bid.max())+1)
+for label, kw in (("AMD", dict(ordering=0)), ("ND plain", dict(ordering=1, nd_leaf=96)), ("ND + blocks", dict(ordering=1, nd_leaf=96, block_id=bid))):
+    S = lib.Symbolic(Kd, **kw); a = S.arrays()
+    mf = MFNumpy(a)
+    with np.errstate(all="ignore"):
+        D = mf.factor(Kd.data, ks.Dsigns)
+    F = oq.QDLDLFactorisation(Kd, ks.Dsigns, perm=a["perm"]); F.refactor()
+    print(f"{label:12s} levels={S.stats['nlevels']:4d} nnzL={S.stats['nnzL']:.3e} flops={S.stats['flops']:.3e} max_front={S.stats['max_front']} | MF nreg={mf.nreg} min|D|={np.nanmin(np.abs(D)):.3e} | qdldl same perm nreg={F.regularize_count}")
