@@ -229,7 +229,19 @@ def main():
     rec.detach()
     replay = [s_ for s_ in rec.steps[1:] if len(s_["rhs"]) == 3] or rec.steps[-1:]
     n, m = solver.data.n, solver.data.m
-    lx, lz = np.zeros(n), np.zeros(m)
+
+    def pinned(a):
+        """copy of `a` in page-locked host memory (the e2e copies are then true DMA transfers)"""
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        v = t.numpy(); v[...] = a
+        pinned.keep.append(t)
+        return v
+    pinned.keep = []
+    for s_ in replay:
+        s_["state"] = {k: pinned(v) for k, v in s_["state"].items()}
+        s_["rhs"] = [(pinned(rx), pinned(rz)) for rx, rz in s_["rhs"]]
+    lx, lz = pinned(np.zeros(n)), pinned(np.zeros(m))
+    ks._rx, ks._rz = pinned(ks._rx), pinned(ks._rz)
     stream = torch.cuda.ExternalStream(ks.ldl.stream_ptr(), device=torch.device("cuda", local))
 
     def step(i):

@@ -511,7 +511,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
             if (h->detail) { h->tm.end(st); h->tm.begin(Timers::PANEL, st); }
             const size_t sm64 = (size_t)(GSM + 2 * PB * (PB + 1)) * sizeof(double);
             for (int kb = 0; kb < B.maxns; kb += PB) {
-                k_diag64<<<B.cnt, 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
+                k_diag64<<<B.cnt, 256, (size_t)(GSM + PB * (PB + 1)) * sizeof(double), st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
                                                    rp, h->d_nreg.p);
                 LAUNCH(h);
                 const int rows_below = B.maxnf - kb - 1;

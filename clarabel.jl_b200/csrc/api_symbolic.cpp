@@ -3,6 +3,8 @@
 #include "symbolic.h"
 #include "api_common.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -15,6 +17,12 @@ thread_local std::vector<int32_t> g_block_hint;     // consumed by the next symb
 SymbolicOptions options_from_settings(const cb200_settings* st) {
     SymbolicOptions o;
     o.block_id = g_block_hint.empty() ? nullptr : g_block_hint.data();
+    if (const char* e = getenv("CB200_RELAX")) {       // tuning aid: "small,z1,z2,z3,maxwidth"
+        double a, b, c, d, w;
+        if (sscanf(e, "%lf,%lf,%lf,%lf,%lf", &a, &b, &c, &d, &w) == 5) {
+            o.relax_small = (int32_t)a; o.relax_z1 = b; o.relax_z2 = c; o.relax_z3 = d; o.max_width = (int32_t)w;
+        }
+    }
     if (st) {
         o.ordering = st->ordering;
         if (st->amd_dense_scale > 0) o.dense_scale = st->amd_dense_scale;

@@ -363,44 +363,120 @@ k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __re
             A[i + j * (PB + 1)] = v;                    // column-major, ld = 65
         }
     __syncthreads();
-    // right-looking LDL' of the block, all 8 warps (warp per trailing column)
+    // ---- blocked LDL' of the 64 x 64 block in 4 panels of 16 columns.  Per panel: the 16 x 16
+    // diagonal sub-block is factored by warp 0 in registers (row per lane, shuffles broadcast the
+    // pivot column), the rows below are solved against it (thread per row) and the trailing part
+    // gets a rank-16 update from all threads: 3 barriers per panel instead of 2 per column.
+    __shared__ double Xs[48 * 17];
+    __shared__ double dvs[PB], dis[PB];
+    __shared__ double Sbuf[3 * 16 * 17];
     const int lane = tid & 31, wid = tid >> 5;
-    for (int k = 0; k < nb; ++k) {
-        double d = A[k + k * (PB + 1)];
-        const double sg = (double)S.dsign[f + J0 + k];
-        bool reg = false;
-        if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
-        const double dinv = 1.0 / d;
-        const double* ck = A + k * (PB + 1);
-        for (int j = k + 1 + wid; j < nb; j += 8) {
-            const double wj = ck[j] * dinv;
-            double* cj = A + j * (PB + 1);
-            for (int i = j + lane; i < nb; i += 32) cj[i] -= ck[i] * wj;
+    constexpr int LDA = PB + 1;
+    for (int e = nb + tid; e < PB; e += 256) A[e + e * LDA] = 1.0;     // pad: identity beyond nb
+    __syncthreads();
+    for (int kb = 0; kb < PB; kb += 16) {
+        if (wid == 0) {
+            const int i = lane & 15;                   // lanes 16..31 mirror 0..15 (only < 16 write)
+            double a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = (j <= i) ? A[(kb + i) + (kb + j) * LDA] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                double d = __shfl_sync(0xffffffffu, a[k], k);
+                const int gk = kb + k;
+                bool reg = false;
+                if (gk < nb) {
+                    const double sg = (double)S.dsign[f + J0 + gk];
+                    if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
+                }
+                const double dinv = 1.0 / d;
+                const double lik = a[k] * dinv;        // L[i][k] for i > k
+#pragma unroll
+                for (int j = k + 1; j < 16; ++j) {
+                    const double ajk = __shfl_sync(0xffffffffu, a[k], j);    // unscaled A[j][k]
+                    if (i >= j) a[j] -= lik * ajk;
+                }
+                if (i > k) a[k] = lik;
+                if (i == k) a[k] = d;
+                if (lane == 0) { dvs[gk] = d; dis[gk] = dinv; if (reg) atomicAdd(nreg, 1u); }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j <= i) A[(kb + i) + (kb + j) * LDA] = a[j];
+            }
         }
         __syncthreads();
-        for (int i = k + 1 + tid; i < nb; i += 256) A[i + k * (PB + 1)] *= dinv;
-        if (tid == 0) {
-            A[k + k * (PB + 1)] = d; D[f + J0 + k] = d; Dinv[f + J0 + k] = dinv;
-            if (reg) atomicAdd(nreg, 1u);
+        const int nbelow = PB - kb - 16;
+        if (tid < nbelow) {                            // x L11' = a ; L = x D^-1 ; X = x (= L D)
+            const int r = kb + 16 + tid;
+            double x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = A[r + (kb + j) * LDA];
+#pragma unroll
+            for (int j = 1; j < 16; ++j) {
+                double v = x[j];
+#pragma unroll
+                for (int l = 0; l < 16; ++l) if (l < j) v -= x[l] * A[(kb + j) + (kb + l) * LDA];
+                x[j] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { Xs[tid * 17 + j] = x[j]; A[r + (kb + j) * LDA] = x[j] * dis[kb + j]; }
+        }
+        __syncthreads();
+        for (int e = tid; e < nbelow * nbelow; e += 256) {
+            const int ii = e % nbelow, jj = e / nbelow;
+            if (ii >= jj) {
+                double acc2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc2 += Xs[ii * 17 + k] * A[(kb + 16 + jj) + (kb + k) * LDA];
+                A[(kb + 16 + ii) + (kb + 16 + jj) * LDA] -= acc2;
+            }
         }
         __syncthreads();
     }
-    // inverse of the unit-lower factor, 4 threads per column j: x_i = -(L_ij + sum_{j<k<i} L_ik x_k);
-    // the k-sum is split over the 4 threads of the group and reduced with shuffles.  X is written
-    // into the upper triangle of A (X[i][j] stored at A[j + i*65], i > j), which the LDL' left unused.
-    {
-        const int j = tid >> 2, part = tid & 3;
-        for (int i = 1; i < PB; ++i) {              // same trip count on every lane (full-mask shuffles)
-            double acc2 = 0.0;
-            if (i > j && i < nb)
-                for (int k = j + 1 + part; k < i; k += 4) acc2 += A[i + k * (PB + 1)] * A[j + k * (PB + 1)];
-            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
-            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
-            if (part == 0 && i > j && i < nb) A[j + i * (PB + 1)] = -(A[i + j * (PB + 1)] + acc2);
-            __syncwarp();
+    for (int k = tid; k < nb; k += 256) { D[f + J0 + k] = dvs[k]; Dinv[f + J0 + k] = dis[k]; }
+    // ---- blocked inverse X = inv(L) of the unit-lower factor (16 x 16 blocks).  X[r][c] (r > c) is
+    // written into the unused upper triangle at A[c + r*LDA].
+    auto Xat = [&](int r, int c) -> double { return r > c ? A[c + r * LDA] : (r == c ? 1.0 : 0.0); };
+    if (tid < PB) {                                    // diagonal blocks: thread = (block I, column j)
+        const int I = tid >> 4, j = tid & 15, o = I * 16;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (k >= j && k < i) v -= A[(o + i) + (o + k) * LDA] * x[k];
+            if (i > j) x[i] = v;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i > j) A[(o + j) + (o + i) * LDA] = x[i];
     }
     __syncthreads();
+    {
+        const int i = tid >> 4, j = tid & 15;          // element of a 16 x 16 block
+        for (int dist = 1; dist < 4; ++dist) {
+            for (int J = 0; J + dist < 4; ++J) {       // S = sum_K L_IK X_KJ
+                const int I = J + dist;
+                double sacc = 0.0;
+                for (int K = J; K < I; ++K)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        sacc += A[(I * 16 + i) + (K * 16 + k) * LDA] * Xat(K * 16 + k, J * 16 + j);
+                Sbuf[J * 16 * 17 + i * 17 + j] = sacc;
+            }
+            __syncthreads();
+            for (int J = 0; J + dist < 4; ++J) {       // X_IJ = -X_II S
+                const int I = J + dist;
+                double xacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) if (k <= i) xacc += Xat(I * 16 + i, I * 16 + k) * Sbuf[J * 16 * 17 + k * 17 + j];
+                A[(J * 16 + j) + (I * 16 + i) * LDA] = -xacc;
+            }
+            __syncthreads();
+        }
+    }
     // park [inv(L_JJ) strictly lower ; d on the diagonal] (column-major 64 x 64)
     double* Wd = Wst + woff[blockIdx.x] + (int64_t)(J0 / PB) * (PB * PB);
     for (int e = tid; e < PB * PB; e += 256) {
