@@ -44,14 +44,17 @@ template <class T> struct DevBuf {
     ~DevBuf() { free(); }
 };
 
-struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0; bool many_children = false; };
+struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpanel = 0; bool many_children = false; };
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
+constexpr int NPANEL = 4;
+static const int kPanelDoubles[NPANEL] = {2048, 6144, 14336, 1 << 30};
 constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
 
 struct LevelPlan {
     Batch small[NSMALL];
+    Batch panel[NPANEL];       // 64 < nf <= 152: panel-in-smem kernel, classes by panel size
     Batch large;
     Batch solve[NSOLVE];
     Batch topf, tops;          // multi-GPU: replicated top fronts of this level (factor / solve)
@@ -186,6 +189,7 @@ struct cb200_handle {
     double last_eps = 0;
     bool resident = false;
     bool detail = false;       // per-kernel-class event timing (disables graph replay)
+    bool use_panel_kernel = true;
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -353,6 +357,7 @@ int build_plans(cb200_handle* h) {
             int nf = S.ns(sn) + S.nr(sn);
             b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
             b.maxnr = std::max(b.maxnr, S.nr(sn));
+            b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn));
             if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
             batches.push_back(sn);
             woff.push_back(large ? w : 0);
@@ -361,7 +366,7 @@ int build_plans(cb200_handle* h) {
         if (large) { P.wtotal += w; wmax = std::max(wmax, w); }
     };
     for (int lv = 0; lv < S.nlevels; ++lv) {
-        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], top;
+        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], pcl[NPANEL], top;
         for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
             int32_t sn = S.level_list[q];
             if (h->dist) {
@@ -370,7 +375,10 @@ int build_plans(cb200_handle* h) {
             }
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
-            cls[c].push_back(sn);
+            if (c >= 3 && c < NSMALL && h->use_panel_kernel) {
+                int pc = 0; while (nf * S.ns(sn) > kPanelDoubles[pc]) ++pc;
+                pcl[pc].push_back(sn);
+            } else cls[c].push_back(sn);
             const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
             const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
             const bool tiny = S.ns(sn) <= SG && nf <= 32;
@@ -380,6 +388,7 @@ int build_plans(cb200_handle* h) {
         LevelPlan& P = h->plan[lv];
         P.wtotal = 0;
         for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
+        for (int c = 0; c < NPANEL; ++c) add_batch(P.panel[c], pcl[c], false, P);
         add_batch(P.large, cls[NSMALL], true, P);
         for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
         add_batch(P.topf, top, true, P);
@@ -485,6 +494,14 @@ int factor_body(cb200_handle* h, bool static_reg) {
         launch_small<256>(h, P.small[3], 96, rp);
         launch_small<256>(h, P.small[4], 128, rp);
         launch_small<256>(h, P.small[5], 160, rp);
+        for (int c = 0; c < NPANEL; ++c) {
+            const Batch& b = P.panel[c];
+            if (!b.cnt) continue;
+            const size_t sm = ((size_t)b.maxpanel + (size_t)b.maxnf * 17 + (size_t)8 * b.maxnf) * sizeof(double);
+            k_factor_panel<<<b.cnt, 256, sm, st>>>(ds, h->d_batches.p + b.off, b.maxpanel, b.maxnf, h->d_L.p, h->d_U.p,
+                                                   h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
+            LAUNCH(h);
+        }
         if (h->detail) h->tm.end(st);
         for (int pass = 0; pass < 2; ++pass) {
             const Batch& B = pass == 0 ? P.large : P.topf;
@@ -691,6 +708,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_asm_colptr.upload(S.asm_colptr, s)); CUDA_OK(h->d_asm_src.upload(S.asm_src, s));
         CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
         // ---- level plans (+ workspace sized for them)
+        h->use_panel_kernel = !(getenv("CB200_NO_PANEL") && getenv("CB200_NO_PANEL")[0] == '1');
         { int rcp = build_plans(h); if (rcp) { delete h; return rcp; } }
         // ---- numeric storage
         CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
@@ -707,6 +725,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(cudaMemsetAsync(h->d_eps.p, 0, sizeof(double), s));
         CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), s));
         // opt in to large dynamic shared memory for the bigger small-front classes
+        CUDA_OK(cudaFuncSetAttribute(k_factor_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (152 * 152 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,

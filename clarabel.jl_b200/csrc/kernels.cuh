@@ -151,6 +151,204 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
     }
 }
 
+// ------------------------------------------------------------------ G4b mid-size fronts (64 < nf <= 152)
+// Only the nf x ns panel lives in shared memory (a front of 128 x 30 needs 31 KB instead of
+// 128 KB => several CTAs per SM); the update block stays in global memory:
+//   1. panel <- scattered K entries ; extend-add: destination columns < ns accumulate into the smem
+//      panel, columns >= ns are summed in a per-warp smem column buffer and written to the update
+//      block (destination-owner lists => fixed summation order);
+//   2. blocked LDL' of the panel in 16-column steps: 16x16 diagonal sub-block in registers of one
+//      warp (shuffles), thread-per-row solve of the rows below, rank-16 update of the remaining
+//      panel columns; sign-based dynamic regularisation per pivot as in QDLDL;
+//   3. Schur complement U -= L21 D L21' with 4x4 register tiles read from the smem panel;
+//   4. inverse of the 64x64 diagonal blocks of L11 (4 threads per column) and write-back.
+// dynamic smem: panel (maxpanel) + Xs (nf x 17) + colbuf (8 x nf) doubles.
+__global__ void __launch_bounds__(256)
+k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int maxnf,
+               double* __restrict__ Lst, double* __restrict__ Ust, double* __restrict__ D,
+               double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
+    extern __shared__ double smem[];
+    __shared__ double dvs[160], dis[160];
+    double* P = smem;                                   // nf x ns, column-major, ld = nf
+    double* Xs = smem + maxpanel;                       // (rows below) x 17
+    double* colbuf = Xs + (size_t)maxnf * 17;           // 8 warps x maxnf
+    const int s = batch[blockIdx.x];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double* Lp = Lst + S.panel_off[s];
+    double* Us = Ust + S.upd_off[s];
+    for (int i = tid; i < nf * ns; i += 256) P[i] = Lp[i];
+    __syncthreads();
+    // ---- 1. extend-add
+    {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        double* cb = colbuf + (size_t)wid * maxnf;
+        for (int d = wid; d < nf; d += 8) {
+            const bool in_panel = d < ns;
+            double* dst = in_panel ? P + d * nf : cb;
+            if (!in_panel) { for (int r = d + lane; r < nf; r += 32) cb[r] = 0.0; __syncwarp(); }
+            for (int e = cp[d]; e < cp[d + 1]; ++e) {
+                const int q = S.asm_src[base + e];
+                const int c = S.asm_child[base + e];
+                const int64_t rp0 = S.rows_ptr[c];
+                const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
+                const int j = (int)(q - rp0);
+                const int32_t* relc = S.rel + rp0;
+                const double* src = Ust + S.upd_off[c] + (int64_t)j * nrc;
+                for (int i = j + lane; i < nrc; i += 32) dst[relc[i]] += src[i];
+                __syncwarp();
+            }
+            if (!in_panel) {
+                double* ucol = Us + (int64_t)(d - ns) * nr - ns;
+                for (int r = d + lane; r < nf; r += 32) ucol[r] = cb[r];
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 2. blocked LDL' of the panel
+    for (int kb = 0; kb < ns; kb += 16) {
+        const int cbk = min(16, ns - kb);
+        if (wid == 0) {
+            const int i = lane & 15;
+            double a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                a[j] = (i < cbk && j <= i) ? P[(kb + i) + (kb + j) * nf] : ((i >= cbk && j == i) ? 1.0 : 0.0);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                double d = __shfl_sync(0xffffffffu, a[k], k);
+                bool reg = false;
+                if (k < cbk) {
+                    const double sg = (double)S.dsign[f + kb + k];
+                    if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
+                }
+                const double dinv = 1.0 / d;
+                const double lik = a[k] * dinv;
+#pragma unroll
+                for (int j = k + 1; j < 16; ++j) {
+                    const double ajk = __shfl_sync(0xffffffffu, a[k], j);
+                    if (i >= j) a[j] -= lik * ajk;
+                }
+                if (i > k) a[k] = lik;
+                if (i == k) a[k] = d;
+                if (lane == 0 && k < cbk) { dvs[kb + k] = d; dis[kb + k] = dinv; if (reg) atomicAdd(nreg, 1u); }
+            }
+            if (lane < 16 && i < cbk) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j <= i) P[(kb + i) + (kb + j) * nf] = a[j];
+            }
+        }
+        __syncthreads();
+        const int r0 = kb + cbk;                        // first row below the diagonal sub-block
+        const int nbelow = nf - r0;
+        if (tid < nbelow) {
+            const int r = r0 + tid;
+            double x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = (j < cbk) ? P[r + (kb + j) * nf] : 0.0;
+#pragma unroll
+            for (int j = 1; j < 16; ++j) {
+                if (j < cbk) {
+                    double v = x[j];
+#pragma unroll
+                    for (int l = 0; l < 16; ++l) if (l < j) v -= x[l] * P[(kb + j) + (kb + l) * nf];
+                    x[j] = v;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                Xs[tid * 17 + j] = x[j];
+                if (j < cbk) P[r + (kb + j) * nf] = x[j] * dis[kb + j];
+            }
+        }
+        __syncthreads();
+        // remaining panel columns jc in [r0, ns): P[i][jc] -= sum_k X[i][k] L[jc][k], i >= jc
+        const int ncols = ns - r0;
+        if (ncols > 0) {
+            for (int jc = wid; jc < ncols; jc += 8) {
+                const int gj = r0 + jc;
+                double lj[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) lj[k] = (k < cbk) ? P[gj + (kb + k) * nf] : 0.0;
+                for (int i = gj + lane; i < nf; i += 32) {
+                    const double* xr = Xs + (i - r0) * 17;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc += xr[k] * lj[k];
+                    P[i + gj * nf] -= acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < ns; k += 256) { D[f + k] = dvs[k]; Dinv[f + k] = dis[k]; }
+    // ---- 3. Schur complement into the (already assembled) update block: 4 x 4 register tiles
+    if (nr > 0) {
+        const int T4 = (nr + 3) >> 2;
+        for (int t = tid; t < T4 * T4; t += 256) {
+            const int ti = t % T4, tj = t / T4;
+            if (ti < tj) continue;
+            const int i0 = ns + ti * 4, j0 = ns + tj * 4;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+            for (int k = 0; k < ns; ++k) {
+                const double dk = dvs[k];
+                double li[4], lj[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    li[a] = (i0 + a < nf) ? P[(i0 + a) + k * nf] : 0.0;
+                    lj[a] = (j0 + a < nf) ? P[(j0 + a) + k * nf] * dk : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] += li[a] * lj[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int gj = j0 + c;
+                if (gj >= nf) continue;
+                double* ucol = Us + (int64_t)(gj - ns) * nr - ns;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int gi = i0 + a;
+                    if (gi < nf && gi >= gj) ucol[gi] -= acc[a][c];
+                }
+            }
+        }
+    }
+    // ---- 4. inverse of every 64 x 64 diagonal block of L11, 4 threads per column; X[i][j] (i > j)
+    // goes to the unused mirror position P[j + i*nf] and is swapped into place at write-back
+    for (int b0 = 0; b0 < ns; b0 += SB) {
+        const int sb = min(SB, ns - b0);
+        const int j = tid >> 2, part = tid & 3;
+        for (int i = 1; i < SB; ++i) {
+            double acc2 = 0.0;
+            if (i > j && i < sb)
+                for (int k = j + 1 + part; k < i; k += 4) acc2 += P[(b0 + i) + (b0 + k) * nf] * P[(b0 + j) + (b0 + k) * nf];
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+            if (part == 0 && i > j && i < sb) P[(b0 + j) + (b0 + i) * nf] = -(P[(b0 + i) + (b0 + j) * nf] + acc2);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * ns; e += 256) {
+        const int i = e % nf, j = e / nf;
+        double v = P[e];
+        if (i < ns && i > j && (i / SB) == (j / SB)) v = P[j + i * nf];     // inverted diagonal block
+        Lp[e] = v;
+    }
+}
+
 // ------------------------------------------------------------------ G6 assembly for large fronts
 // grid (ceil(maxnf / 8), nbatch), 256 threads: one warp per destination column of the front;
 // sources ordered by child (deterministic), no inter-warp conflicts, no barriers.
