@@ -49,8 +49,15 @@ struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpan
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
 constexpr int NPANEL = 4;
-static const int kPanelDoubles[NPANEL] = {2048, 6144, 14336, 1 << 30};
+static const int kPanelDoubles[NPANEL] = {4096, 9000, 16000, 1 << 30};   // smem need classes (doubles)
 constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
+
+// fronts handled by k_factor_panel: 64 < nf <= 152 (panel + scratch in one CTA's shared memory)
+inline bool panel_eligible(int nf, int ns) {
+    // (measured: extending this to narrow fronts up to nf = 320 moves work from the pivot-block
+    // kernels to 1-CTA-per-SM panels and is a net loss on C5, so the range stays 64 < nf <= 152)
+    return nf > 64 && nf <= 152 && ns <= 150 && ((int64_t)nf * ns + (int64_t)nf * 25) <= 27000;
+}
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -357,7 +364,7 @@ int build_plans(cb200_handle* h) {
             int nf = S.ns(sn) + S.nr(sn);
             b.maxnf = std::max(b.maxnf, nf); b.maxns = std::max(b.maxns, S.ns(sn));
             b.maxnr = std::max(b.maxnr, S.nr(sn));
-            b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn));
+            b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn) + 25 * nf);      // smem need of k_factor_panel
             if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
             batches.push_back(sn);
             woff.push_back(large ? w : 0);
@@ -375,8 +382,8 @@ int build_plans(cb200_handle* h) {
             }
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
-            if (c >= 3 && c < NSMALL && h->use_panel_kernel) {
-                int pc = 0; while (nf * S.ns(sn) > kPanelDoubles[pc]) ++pc;
+            if (h->use_panel_kernel && panel_eligible(nf, S.ns(sn))) {
+                int pc = 0; while (nf * S.ns(sn) + 25 * nf > kPanelDoubles[pc]) ++pc;
                 pcl[pc].push_back(sn);
             } else cls[c].push_back(sn);
             const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
@@ -497,7 +504,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
         for (int c = 0; c < NPANEL; ++c) {
             const Batch& b = P.panel[c];
             if (!b.cnt) continue;
-            const size_t sm = ((size_t)b.maxpanel + (size_t)b.maxnf * 17 + (size_t)8 * b.maxnf) * sizeof(double);
+            const size_t sm = (size_t)b.maxpanel * sizeof(double);
             k_factor_panel<<<b.cnt, 256, sm, st>>>(ds, h->d_batches.p + b.off, b.maxpanel, b.maxnf, h->d_L.p, h->d_U.p,
                                                    h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
             LAUNCH(h);
@@ -1121,7 +1128,7 @@ int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
     double schur = 0, panel_large = 0, big_bytes = 0, nlarge = 0;
     for (int32_t sn = 0; sn < S.nsuper; ++sn) {
         const double ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
-        if (nf > kSmallNf[NSMALL - 1]) {
+        if (nf > kSmallNf[NSMALL - 1] && !(h->use_panel_kernel && panel_eligible((int)nf, (int)ns))) {
             nlarge += 1;
             schur += nr * (nr + 1.0) * ns;                 // flops of F22 -= L21 D L21' (lower part)
             for (double k = 0; k < ns; ++k) panel_large += (nf - k) * (nf - k);

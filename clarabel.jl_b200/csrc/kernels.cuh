@@ -169,14 +169,15 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
                double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
     extern __shared__ double smem[];
     __shared__ double dvs[160], dis[160];
-    double* P = smem;                                   // nf x ns, column-major, ld = nf
-    double* Xs = smem + maxpanel;                       // (rows below) x 17
-    double* colbuf = Xs + (size_t)maxnf * 17;           // 8 warps x maxnf
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
     const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int nf = ns + nr;
+    double* P = smem;                                   // nf x ns, column-major, ld = nf
+    double* Xs = smem + (size_t)nf * ns;                // (rows below) x 17
+    double* colbuf = Xs + (size_t)nf * 17;              // 8 warps x nf   (total nf*ns + 25*nf doubles)
+    (void)maxpanel; (void)maxnf;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
@@ -186,7 +187,7 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
     {
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
         const int64_t base = S.asm_base[s];
-        double* cb = colbuf + (size_t)wid * maxnf;
+        double* cb = colbuf + (size_t)wid * nf;
         for (int d = wid; d < nf; d += 8) {
             const bool in_panel = d < ns;
             double* dst = in_panel ? P + d * nf : cb;
@@ -246,8 +247,8 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
         __syncthreads();
         const int r0 = kb + cbk;                        // first row below the diagonal sub-block
         const int nbelow = nf - r0;
-        if (tid < nbelow) {
-            const int r = r0 + tid;
+        for (int t = tid; t < nbelow; t += 256) {
+            const int r = r0 + t;
             double x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = (j < cbk) ? P[r + (kb + j) * nf] : 0.0;
@@ -262,7 +263,7 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                Xs[tid * 17 + j] = x[j];
+                Xs[t * 17 + j] = x[j];
                 if (j < cbk) P[r + (kb + j) * nf] = x[j] * dis[kb + j];
             }
         }
