@@ -169,7 +169,6 @@ struct cb200_handle {
     DevBuf<unsigned int> d_nreg;
     std::vector<LevelPlan> plan;
     std::vector<int32_t> h_batches;
-    std::vector<int64_t> h_woff;
     bool have_diag = false;
     // fused (outer) boundary state
     bool maps_set = false;
@@ -227,11 +226,10 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 #define LAUNCH(h) ((h)->tm.nlaunch += 1)
 
 template <int T>
-int launch_small(cb200_handle* h, const Batch& b, int nfcap, RegParams rp) {
+int launch_small(cb200_handle* h, const Batch& b, int /*class cap*/, RegParams rp) {
     if (b.cnt == 0) return 0;
     const int sbuf = std::min(SB, b.maxns);
     size_t sm = ((size_t)b.maxnf * b.maxnf + (size_t)sbuf * sbuf) * sizeof(double);
-    (void)nfcap;
     k_factor_small<T><<<b.cnt, T, sm, h->stream>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
                                                    h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
     LAUNCH(h);

@@ -1,14 +1,17 @@
 // Device kernels for the B200 KKT path (sm_100a).  FP64 throughout (the reference is Float64
-// end-to-end and its IR tolerance is 1e-13 — src/settings.jl:127-132).
+// end-to-end and its IR tolerance is 1e-13 - src/settings.jl:127-132).
 //
-//   G1  cone -> K value update            k_hs_diag, k_hs_soc_dense, k_soc_expansion
+//   G1  cone -> K value update            k_hs_diag, k_hs_soc_dense, k_soc_expansion, k_soc_D
 //   G2  PSD skron                         k_psd_rrt, k_psd_skron
 //   G3  static regularisation             k_diag_absmax, k_compute_eps, k_shift_diag
-//   G4  small-front LDL' (shared memory)  k_factor_small
-//   G5  large-front blocked LDL'          k_panel_large, k_update_large
-//   G6  extend-add                        (fused in k_factor_small) / k_assemble_large
-//   G7  multifrontal triangular solves    k_fwd, k_bwd, k_pack_perm, k_unpack_perm
-//   G8  symmetric SpMV residual + norm    k_residual
+//   G4  small-front LDL' (shared memory)  k_factor_small (nf <= 64), k_factor_panel (64 < nf <= 152)
+//   G5  large-front blocked LDL'          k_diag64, k_rows64, k_schur_large, k_finish_large
+//                                         (64 x 64 GEMM tile on the FP64 tensor-core path: DMMA m8n8k4)
+//   G6  extend-add                        fused in G4 ; k_assemble_large ; k_assemble_atomic
+//   G7  multifrontal triangular solves    k_fwd_{leaf,sub,warp,cta}, k_bwd_*, k_big_{asm,tri,gemv}_*,
+//                                         k_pack_perm, k_unpack_perm
+//   G8  symmetric SpMV residual + norm    k_residual, k_residual_long
+//   G9  multi-GPU helpers                 k_zero_panels, k_mask_vec  (collectives: api_cuda.cu)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

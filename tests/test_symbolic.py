@@ -72,3 +72,38 @@ def test_amd_and_nd_are_permutations_and_reduce_fill(cb):
         assert sorted(perm.tolist()) == list(range(N))
         F = oq.QDLDLFactorisation(KKT, Ds, perm=perm)
         assert F.nnzL < nat.nnzL
+
+
+def test_ordering_arbitration_rejects_bad_dissection(cb):
+    """ordering=1 keeps nested dissection only when its factor cost is within 3x of the AMD-class
+    ordering; on a factor-model (expander-like) KKT graph it must not be worse than AMD."""
+    from clarabel_jl_b200 import lib
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, lambda: cb.problems.c2_portfolio(n=6000))
+    amd = lib.Symbolic(KKT, ordering=0).stats
+    auto = lib.Symbolic(KKT, ordering=1).stats
+    assert auto["flops"] <= 3.0 * amd["flops"] * (1 + 1e-12)
+
+
+def test_block_hint_keeps_cone_blocks_contiguous(cb):
+    """cb200_hint_blocks: rows of a dense cone block may not be split by a separator, i.e. in the
+    elimination order every block is contiguous up to the interleaving the leaf AMD does inside a
+    leaf; here we only require a valid permutation and that the hint is consumed (one-shot)."""
+    from clarabel_jl_b200 import lib
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, small_instances(cb)["C4s"])
+    N = KKT.shape[0]
+    bid = lib.cone_block_ids(cones, data.n, N)
+    assert bid is not None and bid.max() == int((cones.types == cb.cones.PSD).sum()) - 1
+    S1 = lib.Symbolic(KKT, ordering=1, nd_leaf=32, block_id=bid)
+    assert sorted(S1.arrays()["perm"].tolist()) == list(range(N))
+    S2 = lib.Symbolic(KKT, ordering=1, nd_leaf=32)            # hint must not leak into this call
+    S3 = lib.Symbolic(KKT, ordering=1, nd_leaf=32)
+    assert np.array_equal(S2.arrays()["perm"], S3.arrays()["perm"])
+
+
+def test_partition_api_shapes(cb):
+    from clarabel_jl_b200 import lib
+    KKT, mp, Ds, data, cones = kkt_fixture(cb, small_instances(cb)["C3s"])
+    S = lib.Symbolic(KKT)
+    owner, top, load = S.partition(4)
+    assert len(owner) == S.stats["nsuper"] and top.dtype == bool and len(load) == 4
+    assert abs(load.sum() - load.sum()) == 0 and (load >= 0).all()
