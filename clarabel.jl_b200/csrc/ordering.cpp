@@ -453,19 +453,118 @@ struct NDCtx {
             if (score < bestscore) { bestscore = score; best = l; }
         }
         if (best < 0 || (double)lsize[best] > 0.25 * (double)tot) { amd_leaf(verts); return; }
-        // ---- thin the separator: keep only level-`best` vertices with a neighbour in level best+1
+        // ---- vertex separator from the edge cut between levels `best` and `best+1`: a minimum
+        // vertex cover of the bipartite boundary graph (Koenig: maximum matching by Hopcroft-Karp,
+        // then alternating reachability from the unmatched left vertices).  Never larger than the
+        // one-sided choice "level-`best` vertices that touch level best+1".
         std::vector<int32_t> A, B, Sp;
-        for (int32_t v : q) {
-            int32_t l = (int32_t)(level[v] - base);
-            if (l < best) A.push_back(v);
-            else if (l > best) B.push_back(v);
-            else {
+        {
+            std::vector<int32_t> X, Y;                       // boundary vertices of the two levels
+            for (int32_t v : q) {
+                const int32_t l = (int32_t)(level[v] - base);
+                if (l == best || l == best + 1) local[v] = -1;
+            }
+            for (int32_t v : q) {
+                const int32_t l = (int32_t)(level[v] - base);
+                if (l != best) continue;
                 bool touches = false;
-                for (int64_t p = xadj[v]; p < xadj[v + 1] && !touches; ++p) {
-                    int32_t u = adj[p];
-                    touches = (label[u] == lab && level[u] - base == best + 1);
+                for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                    const int32_t u = adj[p];
+                    if (label[u] == lab && level[u] - base == best + 1) {
+                        touches = true;
+                        if (local[u] < 0) { local[u] = (int32_t)Y.size(); Y.push_back(u); }
+                    }
                 }
-                if (touches) Sp.push_back(v); else A.push_back(v);
+                if (touches) { local[v] = (int32_t)X.size(); X.push_back(v); }
+            }
+            const int32_t nx = (int32_t)X.size(), ny = (int32_t)Y.size();
+            std::vector<int32_t> mx(nx, -1), my(ny, -1), dist(nx);
+            auto ynbr = [&](int32_t xv, auto&& fn) {        // iterate Y-neighbours (local ids) of X[xv]
+                const int32_t v = X[xv];
+                for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                    const int32_t u = adj[p];
+                    if (label[u] == lab && level[u] - base == best + 1) if (!fn(local[u])) return;
+                }
+            };
+            // Hopcroft-Karp
+            std::vector<int32_t> bq;
+            while (true) {
+                bq.clear();
+                for (int32_t i = 0; i < nx; ++i) { if (mx[i] < 0) { dist[i] = 0; bq.push_back(i); } else dist[i] = -1; }
+                bool found = false;
+                for (size_t h = 0; h < bq.size(); ++h) {
+                    const int32_t i = bq[h];
+                    ynbr(i, [&](int32_t yj) {
+                        const int32_t i2 = my[yj];
+                        if (i2 < 0) found = true;
+                        else if (dist[i2] < 0) { dist[i2] = dist[i] + 1; bq.push_back(i2); }
+                        return true;
+                    });
+                }
+                if (!found) break;
+                int32_t augmented = 0;
+                // layered DFS (iterative) from every free left vertex
+                std::vector<int64_t> itp(nx);
+                std::vector<uint8_t> seen(nx, 0);
+                for (int32_t i = 0; i < nx; ++i) itp[i] = xadj[X[i]];
+                for (int32_t r = 0; r < nx; ++r) {
+                    if (mx[r] >= 0) continue;
+                    std::vector<int32_t> path{r};
+                    while (!path.empty()) {
+                        const int32_t i = path.back();
+                        const int32_t v = X[i];
+                        bool advanced = false;
+                        while (itp[i] < xadj[v + 1]) {
+                            const int32_t u = adj[itp[i]++];
+                            if (!(label[u] == lab && level[u] - base == best + 1)) continue;
+                            const int32_t yj = local[u];
+                            const int32_t i2 = my[yj];
+                            if (i2 < 0) {
+                                // augment along the path: path[k] takes the Y vertex it advanced through
+                                int32_t cur_y = yj;
+                                for (size_t k = path.size(); k-- > 0;) {
+                                    const int32_t xi = path[k];
+                                    const int32_t prev_y = mx[xi];
+                                    mx[xi] = cur_y; my[cur_y] = xi;
+                                    cur_y = prev_y;
+                                }
+                                path.clear(); advanced = true; ++augmented; break;
+                            } else if (!seen[i2] && dist[i2] == dist[i] + 1) {
+                                seen[i2] = 1;                // visit once per phase
+                                path.push_back(i2); advanced = true; break;
+                            }
+                        }
+                        if (!advanced && !path.empty()) path.pop_back();
+                    }
+                }
+                if (augmented == 0) break;                   // safety: no progress in this phase
+            }
+            // Koenig: Z = reachable from free X by alternating paths ; cover = (X \ Z) u (Y n Z)
+            std::vector<uint8_t> zx(nx, 0), zy(ny, 0);
+            bq.clear();
+            for (int32_t i = 0; i < nx; ++i) if (mx[i] < 0) { zx[i] = 1; bq.push_back(i); }
+            for (size_t h = 0; h < bq.size(); ++h) {
+                const int32_t i = bq[h];
+                ynbr(i, [&](int32_t yj) {
+                    if (!zy[yj]) {
+                        zy[yj] = 1;
+                        const int32_t i2 = my[yj];
+                        if (i2 >= 0 && !zx[i2]) { zx[i2] = 1; bq.push_back(i2); }
+                    }
+                    return true;
+                });
+            }
+            for (int32_t v : q) {
+                const int32_t l = (int32_t)(level[v] - base);
+                if (l < best) A.push_back(v);
+                else if (l > best + 1) B.push_back(v);
+                else if (l == best) {
+                    const int32_t i = local[v];
+                    if (i >= 0 && !zx[i]) Sp.push_back(v); else A.push_back(v);
+                } else {
+                    const int32_t j = local[v];
+                    if (j >= 0 && zy[j]) Sp.push_back(v); else B.push_back(v);
+                }
             }
         }
         std::vector<int32_t>().swap(verts);
