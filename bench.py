@@ -241,7 +241,6 @@ def main():
         s_["state"] = {k: pinned(v) for k, v in s_["state"].items()}
         s_["rhs"] = [(pinned(rx), pinned(rz)) for rx, rz in s_["rhs"]]
     lx, lz = pinned(np.zeros(n)), pinned(np.zeros(m))
-    ks._rx, ks._rz = pinned(ks._rx), pinned(ks._rz)
     stream = torch.cuda.ExternalStream(ks.ldl.stream_ptr(), device=torch.device("cuda", local))
 
     def step(i):

@@ -960,6 +960,16 @@ int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_e
     return finish_factor(h);
 }
 
+int32_t cb200_setrhs(cb200_handle* h, const double* rhsx, const double* rhsz) {
+    if (!h->maps_set) { set_error("cb200_setrhs: cb200_set_maps not called"); return -2; }
+    if (h->resident) return 0;
+    cudaStream_t st = h->stream;
+    if (h->n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, h->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h->m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, h->m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));        // the caller may overwrite its buffers on return
+    return 0;
+}
+
 int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
                        double* lhsx, double* lhsz, int32_t* ir_rounds) {
     if (!h->maps_set) { set_error("cb200_solve_ir: cb200_set_maps not called"); return -2; }
@@ -967,7 +977,7 @@ int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
     const int64_t N = h->N, n = h->n, m = h->m;
     if (ir_rounds) *ir_rounds = 0;
     if (N == 0) return 0;
-    if (!h->resident) {
+    if (!h->resident && (rhsx || rhsz)) {
         if (n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
         if (m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
     }

@@ -181,7 +181,6 @@ class B200KKTSolver:
         _lib.check(L.cb200_set_maps(h, n, m, self.p, _p(mP), len(mP), _p(mA), len(mA), _p(mH), len(mH),
                                     _p(mD), len(ctype), _p(ctype), _p(cdim), _p(mu), _p(mv), _p(mDD)),
                    "cb200_set_maps")
-        self._rx = np.zeros(n); self._rz = np.zeros(m)
         self.ir_rounds = 0; self.n_solves = 0
 
     def linear_solver_info(self):
@@ -194,8 +193,9 @@ class B200KKTSolver:
                           "cb200_update_cones")
 
     def setrhs(self, rhsx, rhsz):
-        self._rx[:] = rhsx
-        self._rz[:] = rhsz
+        # kktsolver_setrhs!: the right-hand side goes straight to the device (no host staging copy)
+        rx, rz = _c64(rhsx), _c64(rhsz)
+        _lib.check(self.ldl._L.cb200_setrhs(self.ldl._h, _p(rx), _p(rz)), "cb200_setrhs")
 
     def solve(self, lhsx, lhsz):
         if lhsx is not None:
@@ -203,7 +203,7 @@ class B200KKTSolver:
         if lhsz is not None:
             assert lhsz.dtype == np.float64 and lhsz.flags.c_contiguous
         rounds = C.c_int32(0)
-        ok = _lib.check(self.ldl._L.cb200_solve_ir(self.ldl._h, _p(self._rx), _p(self._rz),
+        ok = _lib.check(self.ldl._L.cb200_solve_ir(self.ldl._h, None, None,
                                                    _p(lhsx), _p(lhsz), C.byref(rounds)),
                         "cb200_solve_ir")
         self.ir_rounds += rounds.value; self.n_solves += 1

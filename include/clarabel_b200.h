@@ -122,8 +122,13 @@ int32_t cb200_set_maps(cb200_handle* h, int64_t n, int64_t m, int64_t p,
 int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_eta,
                            const double* soc_d, const double* soc_u, const double* soc_v,
                            const double* psd_R);
+/* kktsolver_setrhs!(ks, rhsx, rhsz) — kktsolver_directldl.jl:313-327: b = [rhsx; rhsz; 0_p].  The
+ * right-hand side is copied to the device here (the caller may reuse its buffers on return);
+ * a following cb200_solve_ir with rhsx == rhsz == NULL solves for it. */
+int32_t cb200_setrhs(cb200_handle* h, const double* rhsx, const double* rhsz);
 /* kktsolver_setrhs! + kktsolver_solve! (+ getlhs) — kktsolver_directldl.jl:313-371, with
- * _iterative_refinement :389-449 on the device.  lhsx / lhsz may be NULL (Julia `nothing`). */
+ * _iterative_refinement :389-449 on the device.  lhsx / lhsz may be NULL (Julia `nothing`);
+ * rhsx == rhsz == NULL: use the right-hand side set by cb200_setrhs. */
 int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
                        double* lhsx, double* lhsz, int32_t* ir_rounds);
 /* kktsolver_update_P!/A! — kktsolver_directldl.jl:374-386 */
