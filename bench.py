@@ -38,6 +38,9 @@ WORKLOADS = {
     "C3": ("c3_socp", {}, {"n": 100000, "ncones": 2000}, "same generator at n=1e5, 2000 cones (1/5)"),
     "C4": ("c4_sdp", {}, {"ncones": 20, "side": 30, "n": 3000, "vars_per_cone": 200},
            "same generator, 20 cones of side 30"),
+    "C4r": ("c4_sdp", {"ncones": 40, "side": 40, "n": 8000, "vars_per_cone": 300},
+            {"ncones": 20, "side": 30, "n": 3000, "vars_per_cone": 200},
+            "reduced C4 (40 PSD cones of side 40); CPU sample: 20 cones of side 30"),
     "C5": ("c5_block_angular", {}, {"nblocks": 2, "nlink": 64},
            "2 of the 64 diagonal blocks with proportionally fewer linking rows (same generator, "
            "nblocks=2, nlink=64): 1/32 of the full instance; CPU time per iteration grows at least "
