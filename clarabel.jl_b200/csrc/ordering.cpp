@@ -19,6 +19,11 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <atomic>
+#include <thread>
+#include <deque>
+#include <exception>
+#include <cstdlib>
 
 #include "ordering.h"
 
@@ -304,10 +309,18 @@ struct NDCtx {
     std::vector<int32_t> label;      // current piece id of each vertex (-1 = already ordered)
     std::vector<int64_t> level;
     std::vector<int32_t> local;
-    std::vector<int32_t> order;
-    int32_t next_label = 1;
+    std::atomic<int32_t> next_label{1};
     int32_t leaf_size;
     double dense_scale;
+    // Sub-pieces are vertex-disjoint, so independent pieces are ordered on separate host threads;
+    // every per-vertex array is only written at the piece's own vertices.  label[] is also READ at
+    // neighbours that may belong to a piece another thread is relabelling: labels are never reused,
+    // so either value compares unequal to this piece's label (relaxed atomics keep that well defined).
+    std::atomic<int32_t> live_threads{1};
+    int32_t max_threads = 1;
+    static constexpr size_t PAR_MIN_VERTS = 20000;
+    int32_t lab_get(int32_t v) const { return __atomic_load_n(&label[v], __ATOMIC_RELAXED); }
+    void lab_set(int32_t v, int32_t l) { __atomic_store_n(&label[v], l, __ATOMIC_RELAXED); }
 
     // BFS inside piece `lab` from `root`; fills queue (visit order) and level[]; returns #levels
     int32_t bfs(int32_t root, int32_t lab, std::vector<int32_t>& q, int64_t stamp_base) {
@@ -317,7 +330,7 @@ struct NDCtx {
             int32_t v = q[h++];
             for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
                 int32_t u = adj[p];
-                if (label[u] != lab || level[u] >= stamp_base) continue;
+                if (lab_get(u) != lab || level[u] >= stamp_base) continue;
                 level[u] = level[v] + 1; maxl = std::max(maxl, level[u]); q.push_back(u);
             }
         }
@@ -330,56 +343,115 @@ struct NDCtx {
         return w;
     }
 
-    void amd_leaf(const std::vector<int32_t>& verts) {
-        int32_t lab = label[verts[0]];
+    void amd_leaf(const std::vector<int32_t>& verts, std::vector<int32_t>& order) {
+        int32_t lab = lab_get(verts[0]);
         if (compressed) {
             // expand to original vertices and order the induced original subgraph
             std::vector<int32_t> ov;
             for (int32_t v : verts) for (int32_t q = mem_ptr[v]; q < mem_ptr[v + 1]; ++q) ov.push_back(mem[q]);
             const int32_t k = (int32_t)ov.size();
-            if (k <= 2) { for (int32_t v : ov) order.push_back(v); for (int32_t v : verts) label[v] = -1; return; }
+            if (k <= 2) { for (int32_t v : ov) order.push_back(v); for (int32_t v : verts) lab_set(v, -1); return; }
             for (int32_t i = 0; i < k; ++i) olocal[ov[i]] = i;
             std::vector<int64_t> lx(k + 1, 0); std::vector<int32_t> la;
             for (int32_t i = 0; i < k; ++i) {
                 const int32_t v = ov[i];
                 for (int64_t p = oxadj[v]; p < oxadj[v + 1]; ++p)
-                    if (label[comp_of[oadj[p]]] == lab) la.push_back(olocal[oadj[p]]);
+                    if (lab_get(comp_of[oadj[p]]) == lab) la.push_back(olocal[oadj[p]]);
                 lx[i + 1] = (int64_t)la.size();
             }
             std::vector<int32_t> lp(k);
             cb200::amd_order_graph(k, lx.data(), la.data(), dense_scale, lp.data());
             for (int32_t i = 0; i < k; ++i) order.push_back(ov[lp[i]]);
-            for (int32_t v : verts) label[v] = -1;
+            for (int32_t v : verts) lab_set(v, -1);
             return;
         }
         int32_t k = (int32_t)verts.size();
-        if (k <= 2) { for (int32_t v : verts) { order.push_back(v); label[v] = -1; } return; }
+        if (k <= 2) { for (int32_t v : verts) { order.push_back(v); lab_set(v, -1); } return; }
         for (int32_t i = 0; i < k; ++i) local[verts[i]] = i;
         std::vector<int64_t> lx(k + 1, 0); std::vector<int32_t> la;
         for (int32_t i = 0; i < k; ++i) {
             int32_t v = verts[i];
             for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p)
-                if (label[adj[p]] == lab) la.push_back(local[adj[p]]);
+                if (lab_get(adj[p]) == lab) la.push_back(local[adj[p]]);
             lx[i + 1] = (int64_t)la.size();
         }
         std::vector<int32_t> lp(k);
         cb200::amd_order_graph(k, lx.data(), la.data(), dense_scale, lp.data());
         for (int32_t i = 0; i < k; ++i) order.push_back(verts[lp[i]]);
-        for (int32_t v : verts) label[v] = -1;
+        for (int32_t v : verts) lab_set(v, -1);
     }
 
-    void emit_vertex(int32_t v) {               // separator vertex -> its original members
+    void emit_vertex(int32_t v, std::vector<int32_t>& order) {   // separator vertex -> its original members
         if (compressed) for (int32_t q = mem_ptr[v]; q < mem_ptr[v + 1]; ++q) order.push_back(mem[q]);
         else order.push_back(v);
-        label[v] = -1;
+        lab_set(v, -1);
     }
 
-    int64_t stamp = 0;     // level stamps grow monotonically so level[] never needs clearing
+    // When the level structure of the whole graph offers no separator (small-world graphs such as
+    // block-angular problems with random linking rows), the result would be the AMD-class ordering
+    // of everything: the caller can ask to be told instead of paying for it twice.
+    bool skip_unsplit = false, unsplit = false;
+    size_t root_size = 0;
+    void leaf_or_skip(const std::vector<int32_t>& verts, std::vector<int32_t>& order) {
+        if (skip_unsplit && verts.size() == root_size) { unsplit = true; return; }
+        amd_leaf(verts, order);
+    }
 
-    void dissect(std::vector<int32_t>& verts) {
+    struct Piece { std::vector<int32_t>* verts; bool leaf; };
+
+    void run_one(const Piece& pc, std::vector<int32_t>& order, int64_t stamp) {
+        if (pc.verts->empty()) return;
+        if (pc.leaf) amd_leaf(*pc.verts, order); else dissect(*pc.verts, order, stamp);
+    }
+
+    // Order independent pieces and concatenate their orderings in list order.  Large pieces get a
+    // thread of their own while the thread budget lasts; the result does not depend on the budget.
+    void run_pieces(std::vector<Piece>& pieces, std::vector<int32_t>& order, int64_t stamp) {
+        const size_t np = pieces.size();
+        size_t nbig = 0;
+        for (auto& pc : pieces) nbig += (!pc.leaf && pc.verts->size() >= PAR_MIN_VERTS);
+        if (nbig < 2 || live_threads.load() >= max_threads) {
+            for (auto& pc : pieces) run_one(pc, order, stamp);
+            return;
+        }
+        std::vector<std::vector<int32_t>> outs(np);
+        std::vector<std::exception_ptr> errs(np);
+        std::vector<std::thread> threads;
+        std::vector<size_t> mine;
+        size_t big_left = nbig;
+        for (size_t i = 0; i < np; ++i) {
+            bool spawned = false;
+            const bool big = !pieces[i].leaf && pieces[i].verts->size() >= PAR_MIN_VERTS;
+            if (big && --big_left > 0) {                      // the last big piece stays on this thread
+                int32_t cur = live_threads.load();
+                while (cur < max_threads && !spawned)
+                    if (live_threads.compare_exchange_weak(cur, cur + 1)) {
+                        threads.emplace_back([this, &pieces, &outs, &errs, i, stamp] {
+                            try { run_one(pieces[i], outs[i], stamp); } catch (...) { errs[i] = std::current_exception(); }
+                            live_threads.fetch_sub(1);
+                        });
+                        spawned = true;
+                    }
+            }
+            if (!spawned) mine.push_back(i);
+        }
+        for (size_t i : mine) {
+            try { run_one(pieces[i], outs[i], stamp); } catch (...) { errs[i] = std::current_exception(); break; }
+        }
+        for (auto& t : threads) t.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+        for (size_t i = 0; i < np; ++i) {
+            order.insert(order.end(), outs[i].begin(), outs[i].end());
+            std::vector<int32_t>().swap(outs[i]);
+        }
+    }
+
+    // level stamps grow monotonically along every root-to-leaf path of the recursion (stamp is
+    // passed by value), so level[] never needs clearing
+    void dissect(std::vector<int32_t>& verts, std::vector<int32_t>& order, int64_t stamp) {
         // verts all carry the same label
-        if (weight_of(verts) <= leaf_size || verts.size() == 1) { amd_leaf(verts); return; }
-        int32_t lab = label[verts[0]];
+        if (weight_of(verts) <= leaf_size || verts.size() == 1) { leaf_or_skip(verts, order); return; }
+        int32_t lab = lab_get(verts[0]);
         // ---- connected components (each handled independently: no separator needed)
         std::vector<int32_t> q;
         {
@@ -393,27 +465,24 @@ struct NDCtx {
                 for (int32_t v : verts)
                     if (level[v] < base) { bfs(v, lab, q, base); comps.emplace_back(q); }
                 std::vector<int32_t>().swap(verts);
-                // small components are batched together into one AMD leaf to limit overhead
+                // small components are batched together into one AMD leaf to limit overhead;
+                // pieces keep their discovery order
+                std::deque<std::vector<int32_t>> smalls;          // stable addresses
                 std::vector<int32_t> small;
+                std::vector<Piece> pieces;
                 for (auto& c : comps) {
                     if (weight_of(c) <= leaf_size) {
                         small.insert(small.end(), c.begin(), c.end());
+                        std::vector<int32_t>().swap(c);
                         if (weight_of(small) > leaf_size) {
-                            int32_t nl = next_label++;
-                            for (int32_t v : small) label[v] = nl;
-                            amd_leaf(small); small.clear();
+                            smalls.emplace_back(std::move(small)); small.clear();
+                            pieces.push_back({&smalls.back(), true});
                         }
-                    } else {
-                        int32_t nl = next_label++;
-                        for (int32_t v : c) label[v] = nl;
-                        dissect(c);
-                    }
+                    } else pieces.push_back({&c, false});
                 }
-                if (!small.empty()) {
-                    int32_t nl = next_label++;
-                    for (int32_t v : small) label[v] = nl;
-                    amd_leaf(small);
-                }
+                if (!small.empty()) { smalls.emplace_back(std::move(small)); pieces.push_back({&smalls.back(), true}); }
+                for (auto& pc : pieces) { const int32_t nl = next_label++; for (int32_t v : *pc.verts) lab_set(v, nl); }
+                run_pieces(pieces, order, stamp);
                 return;
             }
         }
@@ -436,7 +505,7 @@ struct NDCtx {
         stamp += 2 * n + 4;
         nlev = bfs(root, lab, q, stamp);
         int64_t base = stamp;
-        if (nlev < 5) { amd_leaf(verts); return; }
+        if (nlev < 5) { leaf_or_skip(verts, order); return; }
         // ---- choose the smallest level in the middle half (by cumulative vertex count)
         std::vector<int64_t> lsize(nlev, 0);
         int64_t tot = 0;
@@ -452,7 +521,7 @@ struct NDCtx {
             double score = (double)lsize[l] / (0.1 + bal);
             if (score < bestscore) { bestscore = score; best = l; }
         }
-        if (best < 0 || (double)lsize[best] > 0.25 * (double)tot) { amd_leaf(verts); return; }
+        if (best < 0 || (double)lsize[best] > 0.25 * (double)tot) { leaf_or_skip(verts, order); return; }
         // ---- vertex separator from the edge cut between levels `best` and `best+1`: a minimum
         // vertex cover of the bipartite boundary graph (Koenig: maximum matching by Hopcroft-Karp,
         // then alternating reachability from the unmatched left vertices).  Never larger than the
@@ -470,7 +539,7 @@ struct NDCtx {
                 bool touches = false;
                 for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
                     const int32_t u = adj[p];
-                    if (label[u] == lab && level[u] - base == best + 1) {
+                    if (lab_get(u) == lab && level[u] - base == best + 1) {
                         touches = true;
                         if (local[u] < 0) { local[u] = (int32_t)Y.size(); Y.push_back(u); }
                     }
@@ -483,7 +552,7 @@ struct NDCtx {
                 const int32_t v = X[xv];
                 for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
                     const int32_t u = adj[p];
-                    if (label[u] == lab && level[u] - base == best + 1) if (!fn(local[u])) return;
+                    if (lab_get(u) == lab && level[u] - base == best + 1) if (!fn(local[u])) return;
                 }
             };
             // Hopcroft-Karp
@@ -516,7 +585,7 @@ struct NDCtx {
                         bool advanced = false;
                         while (itp[i] < xadj[v + 1]) {
                             const int32_t u = adj[itp[i]++];
-                            if (!(label[u] == lab && level[u] - base == best + 1)) continue;
+                            if (!(lab_get(u) == lab && level[u] - base == best + 1)) continue;
                             const int32_t yj = local[u];
                             const int32_t i2 = my[yj];
                             if (i2 < 0) {
@@ -569,12 +638,12 @@ struct NDCtx {
         }
         std::vector<int32_t>().swap(verts);
         int32_t la = next_label++, lb = next_label++;
-        for (int32_t v : A) label[v] = la;
-        for (int32_t v : B) label[v] = lb;
-        for (int32_t v : Sp) label[v] = -2;            // taken out of both halves
-        dissect(A);
-        dissect(B);
-        for (int32_t v : Sp) emit_vertex(v);
+        for (int32_t v : A) lab_set(v, la);
+        for (int32_t v : B) lab_set(v, lb);
+        for (int32_t v : Sp) lab_set(v, -2);            // taken out of both halves
+        std::vector<Piece> pieces{{&A, false}, {&B, false}};
+        run_pieces(pieces, order, stamp);
+        for (int32_t v : Sp) emit_vertex(v, order);
     }
 };
 
@@ -588,9 +657,10 @@ void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double d
 // block_id (optional, length n): vertices sharing a block id >= 0 form a dense clique (a PSD or
 // dense SOC cone block of the KKT matrix) that no separator may cut: they are contracted to one
 // weighted vertex for the dissection and expanded again for the leaf orderings.
-void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
-                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out) {
-    if (n == 0) return;
+bool nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out,
+                           bool skip_unsplit) {
+    if (n == 0) return true;
     NDCtx C; C.leaf_size = std::max(8, leaf_size); C.dense_scale = dense_scale;
     std::vector<int64_t> cx; std::vector<int32_t> ca;
     bool any_block = false;
@@ -633,7 +703,12 @@ void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, d
     }
     const int32_t gn = C.n;
     C.label.assign(gn, 0); C.level.assign(gn, -1); C.local.assign(gn, 0);
-    C.order.reserve(n);
+    std::vector<int32_t> order; order.reserve(n);
+    {
+        int32_t hw = (int32_t)std::thread::hardware_concurrency();
+        C.max_threads = std::max(1, std::min(hw, 8));
+        if (const char* e = getenv("CB200_ND_THREADS")) C.max_threads = std::max(1, atoi(e));
+    }
     double dthr = dense_scale * 10.0 * std::sqrt((double)n);
     int64_t dense = (int64_t)std::max(16.0, std::min(dthr, (double)n));
     std::vector<int32_t> dense_nodes, verts;
@@ -642,12 +717,15 @@ void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, d
         if (!is_block && C.xadj[i + 1] - C.xadj[i] > dense) { dense_nodes.push_back(i); C.label[i] = -1; }
         else verts.push_back(i);
     }
-    if (!verts.empty()) C.dissect(verts);
+    C.skip_unsplit = skip_unsplit; C.root_size = verts.size();
+    if (!verts.empty()) C.dissect(verts, order, 0);
+    if (C.unsplit) return false;
     std::sort(dense_nodes.begin(), dense_nodes.end(), [&](int32_t a, int32_t b) {
         int64_t da = C.xadj[a + 1] - C.xadj[a], db = C.xadj[b + 1] - C.xadj[b];
         return da < db || (da == db && a < b); });
-    for (int32_t v : dense_nodes) C.emit_vertex(v);
-    for (int32_t k = 0; k < n; ++k) perm_out[k] = C.order[k];
+    for (int32_t v : dense_nodes) C.emit_vertex(v, order);
+    for (int32_t k = 0; k < n; ++k) perm_out[k] = order[k];
+    return true;
 }
 
 }  // namespace cb200

@@ -10,8 +10,11 @@ void amd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double 
                      int32_t* perm_out);
 void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
                     int32_t leaf_size, int32_t* perm_out);
-void nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
-                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out);
+// returns false (perm_out untouched) only when skip_unsplit is set and no separator was found at the
+// top level, i.e. the ordering would have been amd_order_graph of the whole graph
+bool nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                           int32_t leaf_size, const int32_t* block_id, int32_t* perm_out,
+                           bool skip_unsplit = false);
 }  // namespace cb200
 
 extern "C" {

@@ -6,6 +6,12 @@
 #include <numeric>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
+#include <exception>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cb200 {
 
@@ -90,6 +96,14 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
     const int32_t N = (int32_t)N64;
     const int64_t nnzK = colptr[N];
     S.N = N; S.nnzK = nnzK;
+    const bool verbose = getenv("CB200_SYM_VERBOSE") != nullptr;     // phase times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cb200 symbolic] %-28s %8.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+        t_last = t;
+    };
 
     // ---------------------------------------------------------------- 1. fill-reducing order
     std::vector<int32_t> p0(N);
@@ -100,19 +114,45 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
     } else {
         std::vector<int64_t> xadj; std::vector<int32_t> adj;
         build_sym_graph(N, colptr, rowval, xadj, adj);
-        amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
-        if (opt.ordering == 1) {
+        if (opt.ordering != 1) {
+            amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
+        } else {
             // auto: nested dissection (shallow, wide trees for the level-scheduled kernels and the
-            // multi-GPU split) unless it costs more than nd_max_cost_ratio x the AMD-class ordering
+            // multi-GPU split) unless it costs more than nd_max_cost_ratio x the AMD-class ordering.
+            // The two orderings are independent, so they run on two host threads.
             std::vector<int32_t> pn(N), ipa(N), ipn(N);
-            nd_order_graph_blocks(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf, opt.block_id, pn.data());
-            for (int32_t k = 0; k < N; ++k) { ipa[p0[k]] = k; ipn[pn[k]] = k; }
             bool ab = false;
-            const double fa = ordering_cost(N, colptr, rowval, ipa, 1e300, &ab);
-            const double fn = ordering_cost(N, colptr, rowval, ipn, opt.nd_max_cost_ratio * fa, &ab);
-            if (!ab) p0.swap(pn);
+            double fa = 0;
+            std::exception_ptr err;
+            std::atomic<bool> want_cost{true};
+            std::thread amd_thread([&] {
+                try {
+                    amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
+                    if (!want_cost.load()) return;
+                    for (int32_t k = 0; k < N; ++k) ipa[p0[k]] = k;
+                    bool dummy = false;
+                    fa = ordering_cost(N, colptr, rowval, ipa, 1e300, &dummy);
+                } catch (...) { err = std::current_exception(); }
+            });
+            bool split = false;
+            try {
+                split = nd_order_graph_blocks(N, xadj.data(), adj.data(), opt.dense_scale, opt.nd_leaf,
+                                              opt.block_id, pn.data(), /*skip_unsplit=*/true);
+            } catch (...) { amd_thread.join(); throw; }
+            if (!split) want_cost.store(false);              // nothing to arbitrate: AMD it is
+            lap("  nested dissection");
+            amd_thread.join();
+            lap("  wait for amd thread");
+            if (err) std::rethrow_exception(err);
+            if (split) {
+                for (int32_t k = 0; k < N; ++k) ipn[pn[k]] = k;
+                ordering_cost(N, colptr, rowval, ipn, opt.nd_max_cost_ratio * fa, &ab);
+                if (!ab) p0.swap(pn);
+                lap("  nd cost + arbitration");
+            }
         }
     }
+    lap("ordering");
     std::vector<int32_t> ip0(N);
     for (int32_t k = 0; k < N; ++k) ip0[p0[k]] = k;
 
@@ -176,6 +216,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
         }
     }
 
+    lap("etree + column counts");
     // ---------------------------------------------------------------- 3. postorder (big child last)
     std::vector<int32_t> post(N), ipost(N);
     {
@@ -297,6 +338,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
         for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_list[pos[S.sn_parent[s]]++] = s;
     }
 
+    lap("postorder + supernodes");
     // ---------------------------------------------------------------- 6. supernodal row structures
     S.rows_ptr.assign(ns2 + 1, 0);
     {
@@ -337,6 +379,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
         for (int32_t s = 0; s < ns2; ++s) if (S.sn_parent[s] >= 0) S.child_list[pos[S.sn_parent[s]]++] = s;
     }
 
+    lap("row structures");
     // ---------------------------------------------------------------- 7. storage + maps
     S.panel_off.assign(ns2 + 1, 0); S.upd_off.assign(ns2 + 1, 0);
     S.nnzL = 0; S.flops = 0; S.max_front = 0; S.max_width = 0;
@@ -422,6 +465,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             S.a_map[p] = S.panel_off[s] + (int64_t)(c - f) * nf + lr;
         }
 
+    lap("storage + maps");
     // ---------------------------------------------------------------- 8. level sets
     S.sn_level.assign(ns2, 0);
     int32_t nl = 0;

@@ -107,3 +107,31 @@ def test_partition_api_shapes(cb):
     owner, top, load = S.partition(4)
     assert len(owner) == S.stats["nsuper"] and top.dtype == bool and len(load) == 4
     assert abs(load.sum() - load.sum()) == 0 and (load >= 0).all()
+
+
+def test_nd_result_independent_of_host_threads(monkeypatch):
+    """Disjoint pieces of the dissection are ordered on separate host threads (CB200_ND_THREADS);
+    the permutation must not depend on the thread budget.  A 2-D grid is large enough for both
+    halves of the first separators to get a thread each."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from clarabel_jl_b200 import lib
+    g = 260
+    I = sp.identity(g, format="csc")
+    T = sp.diags([np.ones(g - 1)], [1], shape=(g, g), format="csc")
+    K = sp.triu(sp.kron(I, T) + sp.kron(T, I) + sp.identity(g * g), format="csc")
+    n = K.shape[0]
+    cp = np.ascontiguousarray(K.indptr, dtype=np.int64); ri = np.ascontiguousarray(K.indices, dtype=np.int64)
+    perms = []
+    for th in ("1", "4"):
+        monkeypatch.setenv("CB200_ND_THREADS", th)
+        perm = np.empty(n, dtype=np.int64)
+        rc = lib.lib().cb200_order_nd(n, cp.ctypes.data_as(C.c_void_p), ri.ctypes.data_as(C.c_void_p),
+                                      C.c_double(0.3), 64, perm.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.array_equal(np.sort(perm), np.arange(n))
+        perms.append(perm)
+    assert np.array_equal(perms[0], perms[1])
+    # and the dissection really dissected: far less fill than the natural (banded) order
+    S_nd = lib.Symbolic(K, ordering=1, nd_leaf=64).stats
+    S_nat = lib.Symbolic(K, ordering=2).stats
+    assert S_nd["nnzL"] < 0.5 * S_nat["nnzL"]
