@@ -69,8 +69,14 @@ struct LevelPlan {
 };
 
 struct Timers {
-    enum { CONE = 0, FACTOR = 1, SOLVE = 2, SPMV = 3, SCHUR = 4, PANEL = 5, SMALL = 6, ASM = 7, NPH = 8 };
-    double ms[NPH] = {0, 0, 0, 0, 0, 0, 0, 0};
+    enum { CONE = 0, FACTOR = 1, SOLVE = 2, SPMV = 3, SCHUR = 4, PANEL = 5, SMALL = 6, ASM = 7, NCOARSE = 8 };
+    // per-kernel-class segments, recorded only in detail mode 2 (cb200_get_fine_timers)
+    enum { F_SMALL0 = 0, F_PANEL0 = 6, F_ZERO = 10, F_ASM = 11, F_DIAG = 12, F_ROWS = 13, F_SCHUR = 14, F_FINISH = 15,
+           F_PROLOGUE = 16, F_FWD_LEAF = 17, F_FWD_SUB = 18, F_FWD_WARP = 19, F_FWD_CTA = 20, F_FWD_BIG_ASM = 21,
+           F_FWD_BIG_TRI = 22, F_FWD_BIG_GEMV = 23, F_BWD_LEAF = 24, F_BWD_SUB = 25, F_BWD_WARP = 26, F_BWD_CTA = 27,
+           F_BWD_BIG_GEMV = 28, F_BWD_BIG_TRI = 29, F_PERMUTE = 30, F_COMM = 31, NFINE = 32 };
+    static constexpr int NPH = NCOARSE + NFINE;
+    double ms[NPH] = {};
     double nfactor = 0, nsolve = 0, nlaunch = 0;
     std::vector<cudaEvent_t> pool;
     struct Seg { int ph; cudaEvent_t a, b; bool closed; };
@@ -194,7 +200,7 @@ struct cb200_handle {
     DevBuf<double> d_w, d_eta, d_socd, d_socu, d_socv;
     double last_eps = 0;
     bool resident = false;
-    bool detail = false;       // per-kernel-class event timing (disables graph replay)
+    int detail = 0;            // 1: per-phase event timing, 2: also per kernel class (both disable graph replay)
     bool use_panel_kernel = true;
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
@@ -225,9 +231,17 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 #define LAUNCH(h) ((h)->tm.nlaunch += 1)
 
+// times the launches issued while it is alive under one kernel class (detail mode 2 only)
+struct FineScope {
+    cb200_handle* h; bool on;
+    FineScope(cb200_handle* h_, int cls) : h(h_), on(h_->detail >= 2) { if (on) h->tm.begin(Timers::NCOARSE + cls, h->stream); }
+    ~FineScope() { if (on) h->tm.end(h->stream); }
+};
+
 template <int T>
-int launch_small(cb200_handle* h, const Batch& b, int /*class cap*/, RegParams rp) {
+int launch_small(cb200_handle* h, const Batch& b, int cls, RegParams rp) {
     if (b.cnt == 0) return 0;
+    FineScope fs(h, Timers::F_SMALL0 + cls);
     const int sbuf = std::min(SB, b.maxns);
     size_t sm = ((size_t)b.maxnf * b.maxnf + (size_t)sbuf * sbuf) * sizeof(double);
     k_factor_small<T><<<b.cnt, T, sm, h->stream>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
@@ -240,39 +254,50 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     DevSym ds = devsym(h);
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
+        { FineScope fs(h, Timers::F_FWD_LEAF);
         k_fwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
                                                              h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        }
     }
     const Batch& b4 = P.solve[4];
     if (b4.cnt) {
+        { FineScope fs(h, Timers::F_FWD_SUB);
         k_fwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
                                                                    h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        }
     }
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
+        { FineScope fs(h, Timers::F_FWD_WARP);
         k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        }
     }
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
+        { FineScope fs(h, Timers::F_FWD_CTA);
         k_fwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        }
     }
     for (int pass = 0; pass < 2; ++pass) {
         const Batch& b3 = pass == 0 ? P.solve[3] : P.tops;
         if (!b3.cnt) continue;
         const int32_t* bl = h->d_batches.p + b3.off;
+        { FineScope fs(h, Timers::F_FWD_BIG_ASM);
         if (b3.many_children)
             k_big_asm_fwd<32><<<dim3(nblk((int64_t)b3.maxnf * 32, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
         else
             k_big_asm_fwd<1><<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
+        }
         if (pass == 1 && h->dist) {
             // sum the per-rank partial right-hand sides of the replicated top fronts
+            FineScope fs(h, Timers::F_COMM);
             const Symbolic& S = h->S;
             g_nccl.GroupStart();
             for (int32_t sn : h->h_top_by_level[lv]) {
@@ -287,14 +312,16 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
         }
         const int npanel = nblk(b3.maxns, WP);
         for (int pk = 0; pk < npanel; ++pk) {
-            k_big_tri_fwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, h->d_L.p, h->d_y.p);
+            { FineScope fs(h, Timers::F_FWD_BIG_TRI);
+              k_big_tri_fwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, h->d_L.p, h->d_y.p);
+              LAUNCH(h); }
             const int rows_below = b3.maxnf - pk * WP;     // upper bound
             if (rows_below > 0) {
+                FineScope fs(h, Timers::F_FWD_BIG_GEMV);
                 k_big_gemv_fwd<<<dim3(nblk(rows_below, BRT), b3.cnt), 256, 0, h->stream>>>(
                     ds, bl, pk, h->d_L.p, h->d_y.p, h->d_uvec.p);
                 LAUNCH(h);
             }
-            LAUNCH(h);
         }
     }
 }
@@ -309,10 +336,12 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
         for (int pk = npanel - 1; pk >= 0; --pk) {
             const int rows_below = b3.maxnf - pk * WP;
             if (rows_below > 0) {
+                FineScope fs(h, Timers::F_BWD_BIG_GEMV);
                 k_big_gemvT_bwd<<<dim3(nblk(rows_below, BRT), b3.cnt), 256, 0, h->stream>>>(
                     ds, bl, pk, maxtiles, h->d_L.p, h->d_y.p, h->d_partial.p);
                 LAUNCH(h);
             }
+            FineScope fs(h, Timers::F_BWD_BIG_TRI);
             k_big_tri_bwd<<<b3.cnt, 256, 0, h->stream>>>(ds, bl, pk, maxtiles, h->d_L.p, h->d_Dinv.p,
                                                          h->d_partial.p, h->d_y.p);
             LAUNCH(h);
@@ -320,27 +349,35 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     }
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
+        { FineScope fs(h, Timers::F_BWD_CTA);
         k_bwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
+        }
     }
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
+        { FineScope fs(h, Timers::F_BWD_WARP);
         k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
+        }
     }
     const Batch& b4 = P.solve[4];
     if (b4.cnt) {
+        { FineScope fs(h, Timers::F_BWD_SUB);
         k_bwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
                                                                    h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
+        }
     }
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
+        { FineScope fs(h, Timers::F_BWD_LEAF);
         k_bwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
                                                              h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
+        }
     }
 }
 
@@ -470,6 +507,7 @@ template <class F> int run_captured(cb200_handle* h, GraphExec& g, F body, int b
 int factor_body(cb200_handle* h, bool static_reg) {
     cudaStream_t st = h->stream;
     const auto& S = h->S;
+    if (h->detail >= 2) h->tm.begin(Timers::NCOARSE + Timers::F_PROLOGUE, st);
     CUDA_OK(cudaMemsetAsync(h->d_L.p, 0, h->d_L.n * sizeof(double), st));
     CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), st));
     if (h->nnzK) { k_scatter<<<nblk(h->nnzK, 256), 256, 0, st>>>(h->d_nz.p, h->d_amap.p, h->nnzK, h->d_L.p); LAUNCH(h); }
@@ -490,19 +528,21 @@ int factor_body(cb200_handle* h, bool static_reg) {
         k_zero_panels<<<dim3(32, (unsigned)h->h_top_list.size()), 256, 0, st>>>(ds, h->d_top_list.p, h->d_L.p);
         LAUNCH(h);
     }
+    if (h->detail >= 2) h->tm.end(st);
     for (int lv = 0; lv < S.nlevels; ++lv) {
         const LevelPlan& P = h->plan[lv];
         if (h->detail) h->tm.begin(Timers::SMALL, st);
-        launch_small<32>(h, P.small[0], 16, rp);
-        launch_small<64>(h, P.small[1], 32, rp);
-        launch_small<128>(h, P.small[2], 64, rp);
-        launch_small<256>(h, P.small[3], 96, rp);
-        launch_small<256>(h, P.small[4], 128, rp);
-        launch_small<256>(h, P.small[5], 160, rp);
+        launch_small<32>(h, P.small[0], 0, rp);        // size classes kSmallNf[0..5]
+        launch_small<64>(h, P.small[1], 1, rp);
+        launch_small<128>(h, P.small[2], 2, rp);
+        launch_small<256>(h, P.small[3], 3, rp);
+        launch_small<256>(h, P.small[4], 4, rp);
+        launch_small<256>(h, P.small[5], 5, rp);
         for (int c = 0; c < NPANEL; ++c) {
             const Batch& b = P.panel[c];
             if (!b.cnt) continue;
             const size_t sm = (size_t)b.maxpanel * sizeof(double);
+            FineScope fs(h, Timers::F_PANEL0 + c);
             k_factor_panel<<<b.cnt, 256, sm, st>>>(ds, h->d_batches.p + b.off, b.maxpanel, b.maxnf, h->d_L.p, h->d_U.p,
                                                    h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
             LAUNCH(h);
@@ -515,17 +555,21 @@ int factor_body(cb200_handle* h, bool static_reg) {
             const int32_t* bl = h->d_batches.p + B.off;
             const int64_t* wo = h->d_woff.p + B.off;
             if (h->detail) h->tm.begin(Timers::ASM, st);
-            k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)B.maxnr * B.maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
-            k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
-            h->tm.nlaunch += 2;
-            for (int32_t k = 0; k < B.cnt; ++k) {
-                const int32_t sn = h->h_batches[B.off + k];
-                const int32_t nch = S.child_ptr[sn + 1] - S.child_ptr[sn];
-                if (nch > MANY_CHILDREN) { k_assemble_atomic<<<nch, 64, 0, st>>>(ds, sn, h->d_L.p, h->d_U.p); LAUNCH(h); }
-            }
+            { FineScope fs(h, Timers::F_ZERO);
+              k_zero_upd<<<dim3(std::max(1, std::min(64, nblk((int64_t)B.maxnr * B.maxnr, 1024))), B.cnt), 256, 0, st>>>(ds, bl, h->d_U.p);
+              LAUNCH(h); }
+            { FineScope fs(h, Timers::F_ASM);
+              k_assemble_large<<<dim3(nblk(B.maxnf, ASM_CW), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p);
+              LAUNCH(h);
+              for (int32_t k = 0; k < B.cnt; ++k) {
+                  const int32_t sn = h->h_batches[B.off + k];
+                  const int32_t nch = S.child_ptr[sn + 1] - S.child_ptr[sn];
+                  if (nch > MANY_CHILDREN) { k_assemble_atomic<<<nch, 64, 0, st>>>(ds, sn, h->d_L.p, h->d_U.p); LAUNCH(h); }
+              } }
             if (is_top && h->dist) {
                 // root-front assembly across GPUs: every rank holds the contributions of its own
                 // subtrees (rank 0 also the original entries); sum them over NVLink.
+                FineScope fs(h, Timers::F_COMM);
                 std::vector<int32_t> list(h->h_top_by_level[lv]);
                 int rc = allreduce_fronts(h, B, list);
                 if (rc) return rc;
@@ -533,11 +577,13 @@ int factor_body(cb200_handle* h, bool static_reg) {
             if (h->detail) { h->tm.end(st); h->tm.begin(Timers::PANEL, st); }
             const size_t sm64 = (size_t)(GSM + 2 * PB * (PB + 1)) * sizeof(double);
             for (int kb = 0; kb < B.maxns; kb += PB) {
-                k_diag64<<<B.cnt, 256, (size_t)(GSM + PB * (PB + 1)) * sizeof(double), st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
+                { FineScope fs(h, Timers::F_DIAG);
+                  k_diag64<<<B.cnt, 256, (size_t)(GSM + PB * (PB + 1)) * sizeof(double), st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
                                                    rp, h->d_nreg.p);
-                LAUNCH(h);
+                  LAUNCH(h); }
                 const int rows_below = B.maxnf - kb - 1;
                 if (rows_below > 0) {
+                    FineScope fs(h, Timers::F_ROWS);
                     k_rows64<<<dim3(nblk(rows_below, GBM), B.cnt), 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p,
                                                                                      wo, h->d_D.p, h->d_Dinv.p);
                     LAUNCH(h);
@@ -547,11 +593,13 @@ int factor_body(cb200_handle* h, bool static_reg) {
             {
                 const int T = nblk(B.maxnr, GBM);
                 if (T > 0) {
+                    FineScope fs(h, Timers::F_SCHUR);
                     k_schur_large<<<dim3(T * (T + 1) / 2, B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p, h->d_D.p);
                     LAUNCH(h);
                 }
             }
             if (h->detail) h->tm.end(st);
+            FineScope fs(h, Timers::F_FINISH);
             k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
@@ -580,20 +628,27 @@ int sweeps_body(cb200_handle* h) {
 int tri_solve(cb200_handle* h, const double* d_rhs, double* d_sol) {
     cudaStream_t st = h->stream;
     h->tm.begin(Timers::SOLVE, st);
-    if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
-    if (h->dist && h->N) {
-        // top-front entries of the right-hand side are contributed by rank 0 only
-        k_mask_vec<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_topcolkeep.p, h->N); LAUNCH(h);
+    {
+        FineScope fs(h, Timers::F_PERMUTE);
+        if (h->N) { k_pack_perm<<<nblk(h->N, 256), 256, 0, st>>>(d_rhs, h->d_perm.p, h->N, h->d_y.p); LAUNCH(h); }
+        if (h->dist && h->N) {
+            // top-front entries of the right-hand side are contributed by rank 0 only
+            k_mask_vec<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_topcolkeep.p, h->N); LAUNCH(h);
+        }
     }
     int rc = run_captured(h, h->g_solve, [&]() { return sweeps_body(h); });
     if (rc) return rc;
     if (h->dist && h->N) {
         // every rank holds the solution on its own subtrees (+ the replicated top part): gather by
         // zeroing what a rank does not own and summing over NVLink
+        FineScope fs(h, Timers::F_COMM);
         k_mask_vec<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_keepcol.p, h->N); LAUNCH(h);
         NCCL_OK(g_nccl.AllReduce(h->d_y.p, h->d_y.p, (size_t)h->N, ncclDouble, ncclSum, h->comm, st));
     }
-    if (h->N) { k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h); }
+    if (h->N) {
+        FineScope fs(h, Timers::F_PERMUTE);
+        k_unpack_perm<<<nblk(h->N, 256), 256, 0, st>>>(h->d_y.p, h->d_perm.p, h->N, d_sol); LAUNCH(h);
+    }
     h->tm.end(st);
     h->tm.nsolve += 1;
     CUDA_OK(cudaGetLastError());
@@ -1129,7 +1184,20 @@ int32_t cb200_dist_init(cb200_handle* h, int32_t rank, int32_t nranks, const cha
     } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 
-int32_t cb200_set_detail(cb200_handle* h, int32_t on) { h->detail = on != 0; return 0; }
+int32_t cb200_set_detail(cb200_handle* h, int32_t level) { h->detail = level < 0 ? 0 : (level > 2 ? 2 : level); return 0; }
+
+static const char* const kFineNames[Timers::NFINE] = {
+    "factor_small_nf16", "factor_small_nf32", "factor_small_nf64", "factor_small_nf96", "factor_small_nf128",
+    "factor_small_nf152", "factor_panel_c0", "factor_panel_c1", "factor_panel_c2", "factor_panel_c3",
+    "zero_update_blocks", "assemble_large", "diag64", "rows64", "schur_large", "finish_large", "factor_prologue",
+    "fwd_leaf", "fwd_sub", "fwd_warp", "fwd_cta", "fwd_big_assemble", "fwd_big_tri", "fwd_big_gemv",
+    "bwd_leaf", "bwd_sub", "bwd_warp", "bwd_cta", "bwd_big_gemvT", "bwd_big_tri", "permute_vectors", "nccl"};
+
+int32_t cb200_get_fine_timers(cb200_handle* h, double* out_ms, int32_t len) {
+    for (int i = 0; i < len && i < Timers::NFINE; ++i) out_ms[i] = h->tm.ms[Timers::NCOARSE + i];
+    return Timers::NFINE;
+}
+const char* cb200_fine_timer_name(int32_t i) { return (i >= 0 && i < Timers::NFINE) ? kFineNames[i] : ""; }
 
 int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
     const Symbolic& S = h->S;

@@ -100,8 +100,16 @@ class B200DirectLDLSolver:
                     nfactor=int(out[4]), nsolve=int(out[5]), nlaunch=int(out[6]),
                     schur_ms=out[7], panel_ms=out[8], small_ms=out[9], asm_ms=out[10])
 
-    def set_detail(self, on):
-        self._L.cb200_set_detail(self._h, int(bool(on)))
+    def set_detail(self, level):
+        """0 off, 1 (or True) factorisation groups, 2 every kernel class (see fine_timers)."""
+        self._L.cb200_set_detail(self._h, int(level))
+
+    def fine_timers(self):
+        """{kernel class: accumulated ms} recorded while set_detail(2) was on."""
+        n = self._L.cb200_get_fine_timers(self._h, None, 0)
+        out = np.zeros(n)
+        self._L.cb200_get_fine_timers(self._h, _p(out), n)
+        return {self._L.cb200_fine_timer_name(i).decode(): float(out[i]) for i in range(n)}
 
     def stats(self):
         out = np.zeros(10)

@@ -22,7 +22,7 @@ EXPORTED = [
     "cb200_download", "cb200_get_timers", "cb200_reset_timers", "cb200_last_error",
     "cb200_get_stream", "cb200_set_resident",
     "cb200_symbolic_partition", "cb200_nccl_unique_id", "cb200_dist_init",
-    "cb200_set_detail", "cb200_get_stats", "cb200_hint_blocks",
+    "cb200_set_detail", "cb200_get_fine_timers", "cb200_fine_timer_name", "cb200_get_stats", "cb200_hint_blocks",
 ]
 
 
@@ -85,6 +85,8 @@ def lib():
         L.cb200_nccl_unique_id.argtypes = [P]; L.cb200_nccl_unique_id.restype = I32
         L.cb200_dist_init.argtypes = [P, I32, I32, P]; L.cb200_dist_init.restype = I32
         L.cb200_set_detail.argtypes = [P, I32]; L.cb200_set_detail.restype = I32
+        L.cb200_get_fine_timers.argtypes = [P, P, I32]; L.cb200_get_fine_timers.restype = I32
+        L.cb200_fine_timer_name.argtypes = [I32]; L.cb200_fine_timer_name.restype = C.c_char_p
         L.cb200_get_stats.argtypes = [P, P, I32]; L.cb200_get_stats.restype = I32
         L.cb200_hint_blocks.argtypes = [P, I64]; L.cb200_hint_blocks.restype = I32
         _LIB = L

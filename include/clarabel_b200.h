@@ -145,8 +145,14 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len);
  * 8 pivot-block phase (k_diag64 + k_rows64), 9 small fronts (k_factor_small), 10 assembly */
 int32_t cb200_get_timers(cb200_handle* h, double* out, int32_t len);
 int32_t cb200_reset_timers(cb200_handle* h);
-/* per-kernel-class event timing inside the factorisation (disables CUDA-graph replay while on) */
-int32_t cb200_set_detail(cb200_handle* h, int32_t on);
+/* event timing inside the phases (disables CUDA-graph replay while on): level 0 off, 1 the four
+ * factorisation groups of cb200_get_timers, 2 additionally every kernel class of the factorisation
+ * and of the solve sweeps (cb200_get_fine_timers) */
+int32_t cb200_set_detail(cb200_handle* h, int32_t level);
+/* detail level 2: accumulated ms per kernel class; writes min(len, count) values, returns count;
+ * cb200_fine_timer_name(i) names class i.  Reset by cb200_reset_timers. */
+int32_t cb200_get_fine_timers(cb200_handle* h, double* out_ms, int32_t len);
+const char* cb200_fine_timer_name(int32_t i);
 /* symbolic statistics: 0 factor flops (sum of squared column lengths), 1 flops of the large-front
  * Schur GEMMs, 2 flops of the large-front panel phase, 3 nnzL, 4 levels, 5 supernodes, 6 large
  * fronts, 7 panel bytes of the multi-CTA solve class, 8 update-storage bytes, 9 panel-storage bytes */
