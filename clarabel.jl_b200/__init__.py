@@ -10,6 +10,6 @@ interface (the Julia toolchain is absent from this image) and the caller harness
 from . import settings, cones, problemdata, kkt_assembly, kktsystem, solver, problems  # noqa: F401
 from .settings import Settings  # noqa: F401
 from .cones import (ZeroConeT, NonnegativeConeT, SecondOrderConeT, PSDTriangleConeT,  # noqa: F401
-                    CompositeCone)
+                    ExponentialConeT, PowerConeT, GenPowerConeT, CompositeCone)
 from .solver import Solver, STATUS_NAMES  # noqa: F401
 from .kktsystem import register_kktsolver  # noqa: F401

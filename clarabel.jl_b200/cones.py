@@ -16,16 +16,27 @@ cone_api.jl:96-152 (collapsing), cone_types.jl:84-117 (SOC expansion threshold 4
 import numpy as np
 
 SOC_NO_EXPANSION_MAX_SIZE = 4          # cone_types.jl:101
-ZERO, NONNEG, SOC, PSD = 0, 1, 2, 3
+ZERO, NONNEG, SOC, PSD, EXP, POW, GENPOW = 0, 1, 2, 3, 4, 5, 6
 _NAMES = {"ZeroConeT": ZERO, "NonnegativeConeT": NONNEG,
-          "SecondOrderConeT": SOC, "PSDTriangleConeT": PSD}
+          "SecondOrderConeT": SOC, "PSDTriangleConeT": PSD,
+          "ExponentialConeT": EXP, "PowerConeT": POW, "GenPowerConeT": GENPOW}
 _FLOATMAX = float(np.finfo(np.float64).max)
+_SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
 
 
 def ZeroConeT(dim): return ("ZeroConeT", int(dim))
 def NonnegativeConeT(dim): return ("NonnegativeConeT", int(dim))
 def SecondOrderConeT(dim): return ("SecondOrderConeT", int(dim))
 def PSDTriangleConeT(dim): return ("PSDTriangleConeT", int(dim))
+def ExponentialConeT(): return ("ExponentialConeT", 3)
+def PowerConeT(alpha): return ("PowerConeT", 3, float(alpha))
+
+
+def GenPowerConeT(alpha, dim2):
+    alpha = tuple(float(a) for a in alpha)
+    if abs(sum(alpha) - 1.0) > 1e-12 or min(alpha) <= 0:
+        raise ValueError("GenPowerConeT: exponents must be positive and sum to 1")
+    return ("GenPowerConeT", len(alpha) + int(dim2), alpha, int(dim2))
 
 
 def triangular_number(k):
@@ -33,7 +44,7 @@ def triangular_number(k):
 
 
 def _nvars(spec):
-    name, d = spec
+    name, d = spec[0], spec[1]
     return triangular_number(d) if name == "PSDTriangleConeT" else d
 
 
@@ -84,18 +95,34 @@ class CompositeCone:
                 raise ValueError("SOC dimension must be >= 2")
         self.rng_cones = np.concatenate([[0], np.cumsum(self.numels)]).astype(np.int64)
         self.numel = int(self.rng_cones[-1])
-        # sparse-expandable SOCs (dim > 4) have a *diagonal* Hs block
+        # sparse-expandable SOCs (dim > 4) have a *diagonal* Hs block; so have generalised power
+        # cones (always expanded, 3 extra columns: directldl_datamaps.jl:81-99)
         self.is_sparse = (self.types == SOC) & (self.dims > SOC_NO_EXPANSION_MAX_SIZE)
-        diag = (self.types == ZERO) | (self.types == NONNEG) | self.is_sparse
+        self.is_genpow = self.types == GENPOW
+        diag = (self.types == ZERO) | (self.types == NONNEG) | self.is_sparse | self.is_genpow
         blk = np.where(diag, self.numels, (self.numels * (self.numels + 1)) // 2)
         self.rng_blocks = np.concatenate([[0], np.cumsum(blk)]).astype(np.int64)
         self.Hs_is_diagonal = diag
+        # nonsymmetric cones (one small object per cone: they are few and 3-dimensional)
+        from . import nonsymmetric as _ns
+        self.nonsym = []                                  # (cone index, object)
+        for i, sp_ in enumerate(self.specs):
+            if sp_[0] == "ExponentialConeT":
+                self.nonsym.append((i, _ns.ExponentialCone()))
+            elif sp_[0] == "PowerConeT":
+                self.nonsym.append((i, _ns.PowerCone(sp_[2])))
+            elif sp_[0] == "GenPowerConeT":
+                self.nonsym.append((i, _ns.GenPowerCone(sp_[2], sp_[3])))
         deg = np.where(self.types == ZERO, 0,
               np.where(self.types == NONNEG, self.numels,
-              np.where(self.types == SOC, 1, self.dims)))
-        self.degree = int(deg.sum())
-        self.p = 2 * int(self.is_sparse.sum())           # pdim(sparse_maps)
-        self.is_symmetric = True
+              np.where(self.types == SOC, 1,
+              np.where(self.types == PSD, self.dims, 0))))
+        self.degree = int(deg.sum()) + sum(c.degree for _, c in self.nonsym)
+        # expansion columns appended to K, in cone order: 2 per sparse SOC, 3 per genpow cone
+        self.pdims = np.where(self.is_sparse, 2, np.where(self.is_genpow, 3, 0)).astype(np.int64)
+        self.p = int(self.pdims.sum())                   # pdim(sparse_maps)
+        self.is_symmetric = len(self.nonsym) == 0
+        self.allows_primal_dual_scaling = all(c.allows_primal_dual for _, c in self.nonsym)
 
         def _concat_ranges(sel):
             if not sel.any():
@@ -141,6 +168,22 @@ class CompositeCone:
             g["lam"] = np.zeros((k, n))
 
     # ------------------------------------------------------------------ helpers
+    def _ns_items(self):
+        """(cone object, slice into the stacked cone vectors) for every nonsymmetric cone."""
+        for i, c in self.nonsym:
+            yield c, slice(int(self.rng_cones[i]), int(self.rng_cones[i + 1]))
+
+    def unit_initialization(self, z, s):
+        """unit_initialization! (coneops_compositecone.jl:79-90): used instead of the symmetric
+        default start whenever a nonsymmetric cone is present."""
+        z[:] = 0.0; s[:] = 0.0
+        z[self.nn_idx] = 1.0; s[self.nn_idx] = 1.0
+        self.scaled_unit_shift(s, 1.0, "primal")          # SOC: e ; PSD: I   (NN handled above)
+        self.scaled_unit_shift(z, 1.0, "dual")
+        z[self.nn_idx] = 1.0; s[self.nn_idx] = 1.0
+        for c, r in self._ns_items():
+            z[r], s[r] = c.unit_initialization()
+
     def _soc_rep(self, percone):
         return np.repeat(percone, self.soc_dims)
 
@@ -172,7 +215,7 @@ class CompositeCone:
         """coneops_compositecone.jl:29-47; NN/Zero elementwise (δ=1), others mean(e)/e."""
         delta[:] = 1.0
         changed = False
-        for i in np.nonzero((self.types == SOC) | (self.types == PSD))[0]:
+        for i in np.nonzero((self.types != ZERO) & (self.types != NONNEG))[0]:
             a, b = self.rng_cones[i], self.rng_cones[i + 1]
             delta[a:b] = e[a:b].mean() / e[a:b]
             changed = True
@@ -217,9 +260,16 @@ class CompositeCone:
         for g in self.psd_groups:
             g["R"][:] = np.eye(g["n"]); g["Rinv"][:] = np.eye(g["n"])
 
-    def update_scaling(self, s, z, mu):
+    def update_scaling(self, s, z, mu, strategy=0):
         """NT scaling.  NN: coneops_nncone.jl:77-89; SOC: coneops_socone.jl:75-154;
-        PSD: coneops_psdtrianglecone.jl:78-143 (R, Rinv, λ; Hs is formed on the device)."""
+        PSD: coneops_psdtrianglecone.jl:78-143 (R, Rinv, λ; Hs is formed on the device).
+        Nonsymmetric cones: dual or primal-dual scaling per `strategy` (nonsymmetric.py)."""
+        for c, r in self._ns_items():
+            try:
+                if not c.update_scaling(s[r], z[r], mu, strategy):
+                    return False
+            except (ValueError, ZeroDivisionError, FloatingPointError):
+                return False                              # z left the dual cone
         ni = self.nn_idx
         if len(ni):
             self.lam[ni] = np.sqrt(s[ni] * z[ni])
@@ -293,6 +343,8 @@ class CompositeCone:
         for g in self.psd_groups:
             tmp = self._psd_mul_W(g, x, g["R"], "N")
             y[g["idx"]] = self._psd_mul_W_vec(g, tmp, g["R"], "T")
+        for c, r in self._ns_items():
+            y[r] = c.mul_Hs(x[r])
 
     def _psd_mul_W(self, g, x, Rx, tr):
         return self._psd_mul_W_vec(g, x[g["idx"]], Rx, tr, gathered=True, xfull=x)
@@ -351,6 +403,8 @@ class CompositeCone:
         for g in self.psd_groups:
             ds[g["idx"]] = 0.0
             ds[g["idx"][:, g["diagpos"]]] = g["lam"] ** 2
+        for c, r in self._ns_items():
+            ds[r] = c.affine_ds(s[r])
 
     def _soc_circ(self, y, z):
         x = self._soc_rep(y[self.soc_head]) * z + self._soc_rep(z[self.soc_head]) * y
@@ -361,6 +415,9 @@ class CompositeCone:
         """_combined_ds_shift_symmetric! (coneops_symmetric_common.jl:2-36); overwrites
         step_z <- W step_z and step_s <- W^{-T} step_s like the reference."""
         shift[self.zero_idx] = 0.0
+        # nonsymmetric cones read the unscaled affine step: sigma*mu*grad - eta (3rd-order term)
+        for c, r in self._ns_items():
+            shift[r] = c.combined_ds_shift(step_z[r].copy(), step_s[r].copy(), sigma_mu)
         tmp = step_z.copy()
         self.mul_W("N", step_z, tmp)
         tmp = step_s.copy()
@@ -405,8 +462,36 @@ class CompositeCone:
             X = 2 * Zm / (l[:, :, None] + l[:, None, :])
             wv = self._psd_svec(g, X)
             out[g["idx"]] = self._psd_mul_W_vec(g, wv, g["R"], "T")
+        for c, r in self._ns_items():
+            out[r] = ds[r]
 
-    def step_length(self, dz, ds, z, s, alpha_max):
+    def compute_barrier(self, z, s, dz, ds, a):
+        """compute_barrier (coneops_compositecone.jl:246-264) at (z + a dz, s + a ds)."""
+        bar = 0.0
+        ni = self.nn_idx
+        if len(ni):
+            v = (s[ni] + a * ds[ni]) * (z[ni] + a * dz[ni])
+            if np.any(v <= 0):
+                return np.inf
+            bar -= float(np.log(v).sum())
+        if self.nsoc:
+            rs = self._soc_residual(s[self.soc_idx] + a * ds[self.soc_idx])
+            rz = self._soc_residual(z[self.soc_idx] + a * dz[self.soc_idx])
+            if np.any(rs <= 0) or np.any(rz <= 0):
+                return np.inf
+            bar -= float(np.log(rs * rz).sum()) / 2
+        for g in self.psd_groups:
+            for x, dx in ((z, dz), (s, ds)):
+                try:
+                    L = np.linalg.cholesky(self._psd_mat(g, x + a * dx))
+                except np.linalg.LinAlgError:
+                    return np.inf
+                bar -= 2.0 * float(np.log(np.diagonal(L, axis1=1, axis2=2)).sum())
+        for c, r in self._ns_items():
+            bar += c.compute_barrier(z[r], s[r], dz[r], ds[r], a)
+        return bar
+
+    def step_length(self, dz, ds, z, s, alpha_max, settings=None):
         a = alpha_max
         ni = self.nn_idx
         if len(ni):
@@ -429,6 +514,15 @@ class CompositeCone:
                 gam = float(np.linalg.eigvalsh(D).min())
                 if gam < 0:
                     a = min(a, 1.0 / (-gam))
+        if self.nonsym:
+            # back off from full steps slightly so that centrality checks and logarithms do not
+            # fail right at the boundary, then the nonsymmetric cones (compositecone.jl:230-243)
+            a = min(a, 1.0 - _SQRT_EPS)
+            back = settings.linesearch_backtrack_step if settings is not None else 0.8
+            amin = settings.min_terminate_step_length if settings is not None else 1e-4
+            for c, r in self._ns_items():
+                az, as_ = c.step_length(dz[r], ds[r], z[r], s[r], a, amin, back)
+                a = min(a, az, as_)
         return a, a
 
     def _soc_step(self, x, y, amax):
@@ -470,3 +564,19 @@ class CompositeCone:
         return dict(w=self.w, soc_eta=self.soc_eta, soc_d=self.soc_d,
                     soc_u=self.soc_u, soc_v=self.soc_v,
                     psd_R=(np.concatenate(psdR) if psdR else np.zeros(0)))
+
+    def export_nonsymmetric_blocks(self):
+        """K values of the nonsymmetric cones in the order the KKT maps expect them:
+        hs   : per cone in cone order, packed triu of Hs (exp/pow, 6 values) or mu*(d1,d2) (genpow);
+        q,r,p: the genpow expansion columns already scaled by -sqrt(mu)
+               (_csc_update_sparsecone, directldl_datamaps.jl:146-166);  D = (-1,-1,+1) each."""
+        hs, q, r, pp = [], [], [], []
+        for i, c in self.nonsym:
+            if self.types[i] == GENPOW:
+                hs.append(c.hs_diag())
+                sq = -np.sqrt(c.mu)
+                q.append(sq * c.q); r.append(sq * c.r); pp.append(sq * c.p)
+            else:
+                hs.append(c.hs_triu())
+        cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+        return dict(hs=cat(hs), q=cat(q), r=cat(r), p=cat(pp))

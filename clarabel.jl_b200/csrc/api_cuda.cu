@@ -936,6 +936,17 @@ int32_t cb200_set_maps(cb200_handle* h, int64_t n, int64_t m, int64_t p,
                 psd_side.push_back((int32_t)d); psd_roff.push_back(roff); psd_hoff.push_back(hoff);
                 roff += d * d; hoff += ne * (ne + 1) / 2; moff += ne;
                 h->psd_maxn = std::max<int32_t>(h->psd_maxn, (int32_t)d);
+            } else if (t == 4 || t == 5) {
+                // exponential / power cone: dense 3x3 block whose values the caller computes
+                // (coneops_expcone.jl:92-100) and sends through cb200_update_values before
+                // cb200_update_cones; no cone kernel touches these entries
+                if (d != 3) { set_error("cb200_set_maps: exponential / power cones have dimension 3"); return -2; }
+                moff += 3; hoff += 6;
+            } else if (t == 6) {
+                // generalised power cone: diagonal block + expansion columns, all sent by the
+                // caller through cb200_update_values (coneops_genpowcone.jl:91-108,
+                // directldl_datamaps.jl:146-166)
+                moff += d; hoff += d;
             } else { set_error("cb200_set_maps: unsupported cone type"); return -2; }
         }
         if (moff != m || hoff != nHs) { set_error("cb200_set_maps: cone table inconsistent with m / nHs"); return -2; }

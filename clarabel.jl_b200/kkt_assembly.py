@@ -23,6 +23,7 @@ class LDLDataMap:
     def __init__(self):
         self.P = self.A = self.Hsblocks = None
         self.soc_u = self.soc_v = self.soc_D = None      # concatenated over sparse SOCs
+        self.gp_q = self.gp_r = self.gp_p = self.gp_D = None   # ... over generalised power cones
         self.diagP = self.diag_full = None
 
 
@@ -56,11 +57,21 @@ def assemble_kkt_matrix(P, A, cones):
         else:
             blk_in_col[a:b] = np.arange(1, b - a + 1)       # dense triu triangle
     cc[n:n + m] += blk_in_col
+    # expansion columns follow in cone order (directldl_kkt_assembly.jl:86-99): v,u per sparse SOC,
+    # q,r,p per generalised power cone; pcol[i] = first expansion column of cone i
+    pdims = getattr(cones, "pdims", np.where(cones.is_sparse, 2, 0))
+    pcol = n + m + np.concatenate([[0], np.cumsum(pdims)]).astype(np.int64)
     sparse_cones = np.nonzero(cones.is_sparse)[0]
-    for k, i in enumerate(sparse_cones):
+    genpow_cones = np.nonzero(getattr(cones, "is_genpow", np.zeros(ncone, dtype=bool)))[0]
+    for i in sparse_cones:
         dim = rc[i + 1] - rc[i]
-        cc[n + m + 2 * k] = dim + 1                          # v column + D
-        cc[n + m + 2 * k + 1] = dim + 1                      # u column + D
+        cc[pcol[i]] = dim + 1                                # v column + D
+        cc[pcol[i] + 1] = dim + 1                            # u column + D
+    for i in genpow_cones:
+        dim = int(rc[i + 1] - rc[i]); dim2 = cones.specs[i][3]; dim1 = dim - dim2
+        cc[pcol[i]] = dim1 + 1                               # q column + D
+        cc[pcol[i] + 1] = dim2 + 1                           # r column + D
+        cc[pcol[i] + 2] = dim + 1                            # p column + D
     colptr = np.concatenate([[0], np.cumsum(cc)]).astype(np.int64)
     nnzK = int(colptr[-1])
     rowval = np.empty(nnzK, dtype=np.int64)
@@ -103,10 +114,10 @@ def assemble_kkt_matrix(P, A, cones):
     mp.Hsblocks = Hs
     # --- sparse SOC expansion columns: v first, then u (directldl_datamaps.jl:42-59)
     us, vs, Ds = [], [], []
-    for k, i in enumerate(sparse_cones):
+    for i in sparse_cones:
         a, b = int(rc[i]), int(rc[i + 1])
         dim = b - a
-        cv, cu = n + m + 2 * k, n + m + 2 * k + 1
+        cv, cu = int(pcol[i]), int(pcol[i]) + 1
         dv = colptr[cv] + np.arange(dim); du = colptr[cu] + np.arange(dim)
         rowval[dv] = n + np.arange(a, b); rowval[du] = n + np.arange(a, b)
         rowval[colptr[cv] + dim] = cv; rowval[colptr[cu] + dim] = cu
@@ -116,15 +127,44 @@ def assemble_kkt_matrix(P, A, cones):
     mp.soc_u = np.concatenate(us) if us else z
     mp.soc_v = np.concatenate(vs) if vs else z
     mp.soc_D = np.concatenate(Ds) if Ds else z
+    # --- generalised power cone expansion columns: q (rows of u), r (rows of w), p (all rows)
+    # (directldl_datamaps.jl:124-144)
+    qs, rs, ps, gD = [], [], [], []
+    for i in genpow_cones:
+        a, b = int(rc[i]), int(rc[i + 1])
+        dim = b - a; dim2 = cones.specs[i][3]; dim1 = dim - dim2
+        cq, cr, cp_ = int(pcol[i]), int(pcol[i]) + 1, int(pcol[i]) + 2
+        dq = colptr[cq] + np.arange(dim1); dr = colptr[cr] + np.arange(dim2); dp = colptr[cp_] + np.arange(dim)
+        rowval[dq] = n + a + np.arange(dim1)
+        rowval[dr] = n + a + dim1 + np.arange(dim2)
+        rowval[dp] = n + a + np.arange(dim)
+        for c_, cnt in ((cq, dim1), (cr, dim2), (cp_, dim)):
+            rowval[colptr[c_] + cnt] = c_
+        qs.append(dq); rs.append(dr); ps.append(dp)
+        gD.append(np.array([colptr[cq] + dim1, colptr[cr] + dim2, colptr[cp_] + dim], dtype=np.int64))
+    mp.gp_q = np.concatenate(qs) if qs else z
+    mp.gp_r = np.concatenate(rs) if rs else z
+    mp.gp_p = np.concatenate(ps) if ps else z
+    mp.gp_D = np.concatenate(gD) if gD else z
     mp.diag_full = colptr[1:] - 1
     mp.diagP = colptr[1:n + 1] - 1
     K = sp.csc_matrix((nzval, rowval, colptr), shape=(N, N))
     return K, mp
 
 
-def fill_Dsigns(m, n, p):
-    """_fill_Dsigns! (kktsolver_directldl.jl:112-126); SOC expansion signs are (-1,+1)."""
+def fill_Dsigns(m, n, p, cones=None):
+    """_fill_Dsigns! (kktsolver_directldl.jl:112-126); expansion signs are (-1,+1) per sparse SOC
+    and (-1,-1,+1) per generalised power cone (directldl_datamaps.jl:21,98), in cone order."""
     D = np.ones(n + m + p, dtype=np.int64)
     D[n:n + m] = -1
-    D[n + m::2] = -1
+    if cones is None or not getattr(cones, "is_genpow", np.zeros(1, dtype=bool)).any():
+        D[n + m::2] = -1
+        return D
+    k = n + m
+    for pd in cones.pdims:
+        if pd == 2:
+            D[k] = -1
+        elif pd == 3:
+            D[k] = -1; D[k + 1] = -1
+        k += int(pd)
     return D

@@ -148,6 +148,22 @@ def dist_init_from_torch(ldl):
     ldl.dist_init(rank, world, obj[0])
 
 
+def nonsym_update_index(mp, cones):
+    """0-based K.data positions of every value the nonsymmetric cones own, in the order
+    nonsym_update_values() lists them: Hs blocks in cone order, then genpow q, r, p, D."""
+    hs = [mp.Hsblocks[cones.rng_blocks[i]:cones.rng_blocks[i + 1]] for i, _ in cones.nonsym]
+    return _i64(np.concatenate(hs + [mp.gp_q, mp.gp_r, mp.gp_p, mp.gp_D]))
+
+
+def nonsym_update_values(mp, cones):
+    """The matching K values: -Hs (get_Hs! then `values *= -1`, kktsolver_directldl.jl:219-226),
+    the expansion columns scaled by -sqrt(mu) and D = (-1,-1,+1) (directldl_datamaps.jl:146-166)."""
+    blk = cones.export_nonsymmetric_blocks()
+    ngp = len(mp.gp_D) // 3
+    return _c64(np.concatenate([-blk["hs"], blk["q"], blk["r"], blk["p"],
+                                np.tile([-1.0, -1.0, 1.0], ngp)]))
+
+
 class B200KKTSolver:
     """OUTER boundary: AbstractKKTSolver over the fused C-ABI entry points."""
 
@@ -156,7 +172,7 @@ class B200KKTSolver:
         self.settings = settings
         self.KKT, self.map = assemble_kkt_matrix(P, A, cones)
         self.p = cones.p
-        self.Dsigns = fill_Dsigns(m, n, self.p)
+        self.Dsigns = fill_Dsigns(m, n, self.p, cones)
         # Ordering choice.  Nested dissection gives the shallow, wide trees the level-scheduled
         # kernels want, but its separators can cut through the dense clique of a PSD cone block;
         # late in the IP iteration those blocks have a dynamic range > 1e10 and a split clique was
@@ -195,6 +211,12 @@ class B200KKTSolver:
         return self.ldl.info()
 
     def update(self, cones):
+        if getattr(cones, "nonsym", None):
+            # exp / pow / genpow blocks are host-computed (their scaling is not an NT scaling):
+            # -Hs, the scaled expansion columns and D go in with one update_values! call
+            if not hasattr(self, "_ns_idx"):
+                self._ns_idx = nonsym_update_index(self.map, cones)
+            self.ldl.update_values(self._ns_idx, nonsym_update_values(self.map, cones))
         st = cones.export_state()
         arrs = [_c64(st[k]) for k in ("w", "soc_eta", "soc_d", "soc_u", "soc_v", "psd_R")]
         return _lib.check(self.ldl._L.cb200_update_cones(self.ldl._h, *[_p(a) for a in arrs]),

@@ -1,8 +1,10 @@
 """Interior-point driver: the *caller* of the KKT path.
 
 Mirror of src/solver.jl (setup! :75-153, solve! :189-380, default start :383-404, strategy
-checkpoints :453-514), src/variables.jl, src/residuals.jl, src/info.jl and src/solution.jl —
-restricted to symmetric cones (Zero/NN/SOC/PSD), which is what every BASELINE config uses.
+checkpoints :453-514), src/variables.jl, src/residuals.jl, src/info.jl and src/solution.jl,
+for symmetric cones (Zero/NN/SOC/PSD: every BASELINE config) and for the nonsymmetric ones
+(exponential / power / generalised power: unit initialisation, primal-dual vs dual scaling
+strategy with the reference's strategy checkpoints, barrier-limited steps).
 It exists because "identical status codes / objectives" can only be judged through whole
 solves and the reference's Julia loop cannot run here.  The loop is backend-agnostic: the
 KKT solver is whatever `settings.direct_solve_method` names (kktsystem.py registry).
@@ -17,6 +19,7 @@ from .settings import Settings
 from .cones import CompositeCone
 from .problemdata import ProblemData
 from .kktsystem import DefaultKKTSystem
+from .nonsymmetric import PRIMAL_DUAL, DUAL
 
 # statuscodes.jl:24-36
 (UNSOLVED, SOLVED, PRIMAL_INFEASIBLE, DUAL_INFEASIBLE, ALMOST_SOLVED,
@@ -200,16 +203,40 @@ class Solver:
         self.variables.copy_from(self.prev_vars)
 
     # ------------------------------------------------------------- variables
-    def _calc_step_length(self, steptype):
-        """variables_calc_step_length (variables.jl:14-46)."""
+    def _calc_step_length(self, steptype, scaling=PRIMAL_DUAL):
+        """solver_get_step_length (solver.jl:407-422) = variables_calc_step_length
+        (variables.jl:14-46) + the barrier limit for nonsymmetric cones under dual scaling."""
         v, step = self.variables, self.step_lhs
         a_tau = -v.tau / step.tau if step.tau < 0 else _FLOATMAX
         a_kap = -v.kappa / step.kappa if step.kappa < 0 else _FLOATMAX
         a = min(a_tau, a_kap, 1.0)
-        az, as_ = self.cones.step_length(step.z, step.s, v.z, v.s, a)
+        az, as_ = self.cones.step_length(step.z, step.s, v.z, v.s, a, self.settings)
         a = min(az, as_)
         if steptype == "combined":
             a *= self.settings.max_step_fraction
+        if (not self.cones.is_symmetric) and steptype == "combined" and scaling == DUAL:
+            a = self._backtrack_step_to_barrier(a)
+        return a
+
+    def _barrier(self, a):
+        """variables_barrier (variables.jl:46-72)."""
+        v, step, cones = self.variables, self.step_lhs, self.cones
+        coef = cones.degree + 1
+        tau, kap = v.tau + a * step.tau, v.kappa + a * step.kappa
+        sz = float((v.z + a * step.z) @ (v.s + a * step.s))
+        mu = (sz + tau * kap) / coef
+        if mu <= 0 or tau <= 0 or kap <= 0:
+            return np.inf
+        return (coef * np.log(mu) - np.log(tau) - np.log(kap)
+                + cones.compute_barrier(v.z, v.s, step.z, step.s, a))
+
+    def _backtrack_step_to_barrier(self, a):
+        """solver_backtrack_step_to_barrier (solver.jl:425-442)."""
+        back = self.settings.linesearch_backtrack_step
+        for _ in range(50):
+            if self._barrier(a) < 1.0:
+                return a
+            a *= back
         return a
 
     def _shift_to_cone_interior(self, z, pd):
@@ -226,7 +253,13 @@ class Solver:
             cones.scaled_unit_shift(z, 0.0, pd)
 
     def _default_start(self):
-        """solver_default_start! (solver.jl:383-404), symmetric branch."""
+        """solver_default_start! (solver.jl:383-404)."""
+        if not self.cones.is_symmetric:
+            # variables_unit_initialization! (variables.jl:213-226)
+            v = self.variables
+            self.cones.unit_initialization(v.z, v.s)
+            v.x[:] = 0.0; v.tau = 1.0; v.kappa = 1.0
+            return
         self.cones.set_identity_scaling()
         self.kktsystem.update(self.data, self.cones)
         self.kktsystem.solve_initial_point(self.variables, self.data)
@@ -253,6 +286,8 @@ class Solver:
         self._default_start()
         tm["default start"] = time.perf_counter() - t
         self.iter_log = []
+        sym = cones.is_symmetric
+        scaling = PRIMAL_DUAL if cones.allows_primal_dual_scaling else DUAL
         while True:
             r.update(v, data)
             mu = (r.dot_sz + v.tau * v.kappa) / (cones.degree + 1)
@@ -265,11 +300,16 @@ class Solver:
                       f"gap {info.gap_abs:.2e} pres {info.res_primal:.2e} dres {info.res_dual:.2e} "
                       f"k/t {info.ktratio:.2e} mu {mu:.2e} step {alpha:.2e}")
             if self._check_termination(it):
+                # _strategy_checkpoint_insufficient_progress (solver.jl:453-472)
                 if info.status == INSUFFICIENT_PROGRESS:
                     self._reset_to_prev()
+                    if (not sym) and scaling == PRIMAL_DUAL:
+                        info.status = UNSOLVED
+                        scaling = DUAL
+                        continue
                 break
             t = time.perf_counter()
-            ok_scale = cones.update_scaling(v.s, v.z, mu)
+            ok_scale = cones.update_scaling(v.s, v.z, mu, scaling)
             tm["scale cones"] += time.perf_counter() - t
             if not ok_scale:
                 info.status = NUMERICAL_ERROR
@@ -288,7 +328,7 @@ class Solver:
                 ok = self.kktsystem.solve(self.step_lhs, d, data, v, cones, "affine")
                 tm["kkt solve"] += time.perf_counter() - t
             if ok:
-                alpha = self._calc_step_length("affine")
+                alpha = self._calc_step_length("affine", scaling)
                 sigma = (1.0 - alpha) ** 3
                 mm = 1.0 if it > 1 else alpha
                 # combined step rhs (variables.jl:125-168)
@@ -306,10 +346,19 @@ class Solver:
                 ok = self.kktsystem.solve(self.step_lhs, d, data, v, cones, "combined")
                 tm["kkt solve"] += time.perf_counter() - t
             if not ok:
-                info.status = NUMERICAL_ERROR
+                # _strategy_checkpoint_numerical_error (solver.jl:475-489)
                 alpha = 0.0
+                if (not sym) and scaling == PRIMAL_DUAL:
+                    scaling = DUAL
+                    continue
+                info.status = NUMERICAL_ERROR
                 break
-            alpha = self._calc_step_length("combined")
+            alpha = self._calc_step_length("combined", scaling)
+            # _strategy_checkpoint_small_step (solver.jl:492-505)
+            if (not sym) and scaling == PRIMAL_DUAL and alpha < st.min_switch_step_length:
+                scaling = DUAL
+                alpha = 0.0
+                continue
             if alpha <= max(0.0, st.min_terminate_step_length):
                 info.status = INSUFFICIENT_PROGRESS
                 alpha = 0.0

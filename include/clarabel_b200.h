@@ -108,8 +108,13 @@ int32_t cb200_info(const cb200_handle* h, int64_t* nnzA, int64_t* nnzL, int32_t*
 /* ---------------------------------------------------------------- OUTER boundary (fused)
  * cb200_set_maps: once after create; uploads LDLDataMap (directldl_datamaps.jl:170-214) and the
  * cone table (CompositeCone.rng_cones / rng_blocks, compositecone_type.jl:96-141).
- *   cone_type[i]: 0 Zero, 1 Nonnegative, 2 SecondOrder, 3 PSDTriangle ; cone_dim[i]: dim (PSD: side n)
- *   map_soc_u / map_soc_v: concatenated over sparse SOCs (dim > 4) in cone order; map_soc_D: 2 each. */
+ *   cone_type[i]: 0 Zero, 1 Nonnegative, 2 SecondOrder, 3 PSDTriangle, 4 Exponential, 5 Power,
+ *                 6 GenPower ; cone_dim[i]: dim (PSD: side n)
+ *   map_soc_u / map_soc_v: concatenated over sparse SOCs (dim > 4) in cone order; map_soc_D: 2 each.
+ *   Nonsymmetric cones (types 4-6): their Hs block (3x3 for exp/pow, coneops_expcone.jl:92-100;
+ *   diagonal + expansion columns for genpow, directldl_datamaps.jl:146-166) is the output of the
+ *   caller's update_scaling!; the caller sends those few values with cb200_update_values right
+ *   before cb200_update_cones, which leaves the entries untouched. */
 int32_t cb200_set_maps(cb200_handle* h, int64_t n, int64_t m, int64_t p,
                        const int64_t* map_P, int64_t nnzP, const int64_t* map_A, int64_t nnzA,
                        const int64_t* map_Hs, int64_t nHs, const int64_t* map_diag_full,

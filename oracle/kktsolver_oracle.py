@@ -124,6 +124,18 @@ def get_Hs(cones, Hsblocks):
             Hs = skron_triu(R @ R.T)
             ti, tj = np.tril_indices(Hs.shape[0])
             blk[:] = Hs[tj, ti]                       # pack_triu: column-major upper
+    # nonsymmetric cones: exp / pow store pack_triu(K.Hs) (coneops_expcone.jl:92-100,
+    # coneops_powcone.jl), genpow the diagonal mu*(d1, d2) (coneops_genpowcone.jl:91-108)
+    for i, c in getattr(cones, "nonsym", ()):
+        blk = Hsblocks[rb[i]:rb[i + 1]]
+        if cones.types[i] == pk.GENPOW:
+            blk[:c.dim1] = c.mu * c.d1
+            blk[c.dim1:] = c.mu * c.d2
+        else:
+            h = 0
+            for col in range(3):
+                for row in range(col + 1):
+                    blk[h] = c.Hs[row, col]; h += 1
     return Hsblocks
 
 
@@ -146,7 +158,7 @@ class OracleDirectLDLKKTSolver:
         N = n + m + self.p
         self.x = np.zeros(N); self.b = np.zeros(N)
         self.work1 = np.zeros(N); self.work2 = np.zeros(N)
-        self.Dsigns = pkg.kkt_assembly.fill_Dsigns(m, n, self.p)
+        self.Dsigns = pkg.kkt_assembly.fill_Dsigns(m, n, self.p, cones)
         self.Hsblocks = np.zeros(int(cones.rng_blocks[-1]))
         self.diagonal_regularizer = 0.0
         st = settings
@@ -175,7 +187,18 @@ class OracleDirectLDLKKTSolver:
         self.Hsblocks *= -1.0
         self._update_values(mp.Hsblocks, self.Hsblocks)
         # sparse SOC expansions (directldl_datamaps.jl:61-79)
-        if cones.p and not self.literal_soc_updates:
+        if getattr(cones, "is_genpow", np.zeros(1, dtype=bool)).any():
+            # generalised power cones (_csc_update_sparsecone, directldl_datamaps.jl:146-166):
+            # columns q, r, p take the vectors, are scaled by -sqrt(mu), D = (-1, -1, +1)
+            oq = orr = op = 0
+            for k, (i, c) in enumerate((i, c) for i, c in cones.nonsym if cones.types[i] == _pkg().cones.GENPOW):
+                iq = mp.gp_q[oq:oq + c.dim1]; ir = mp.gp_r[orr:orr + c.dim2]; ip = mp.gp_p[op:op + c.dim]
+                self._update_values(iq, c.q); self._update_values(ir, c.r); self._update_values(ip, c.p)
+                sq = -np.sqrt(c.mu)
+                self._scale_values(iq, sq); self._scale_values(ir, sq); self._scale_values(ip, sq)
+                self._update_values(mp.gp_D[3 * k:3 * k + 3], np.array([-1.0, -1.0, 1.0]))
+                oq += c.dim1; orr += c.dim2; op += c.dim
+        if cones.nsoc and cones.soc_sparse.any() and not self.literal_soc_updates:
             # same arithmetic as the per-cone loop below (nzval = u; nzval *= -eta^2 is bitwise
             # u * (-eta^2)), issued once over the concatenated maps so that 1e4 cones do not cost
             # 5e4 Python-level calls in the CPU baseline
@@ -186,7 +209,7 @@ class OracleDirectLDLKKTSolver:
             self._update_values(mp.soc_v, cones.soc_v[mask] * neg)
             D = np.empty(2 * len(eta2)); D[0::2] = -eta2; D[1::2] = eta2
             self._update_values(mp.soc_D, D)
-        elif cones.p:
+        elif cones.nsoc and cones.soc_sparse.any():
             off = 0
             ks = 0
             sparse_ids = np.nonzero(cones.soc_sparse)[0]
