@@ -34,8 +34,11 @@ class ProblemData:
         self.b = np.minimum(np.array(b, dtype=np.float64), INFINITY)
         self.cones = cones
         self.m, self.n = A.shape
+        self.dropped_zeros = False
         if settings.input_sparse_dropzeros:
+            nz0 = self.P.nnz + self.A.nnz
             self.P.eliminate_zeros(); self.A.eliminate_zeros()
+            self.dropped_zeros = (self.P.nnz + self.A.nnz) != nz0
         n, m = self.n, self.m
         self.d = np.ones(n); self.dinv = np.ones(n)
         self.e = np.ones(m); self.einv = np.ones(m)
@@ -45,9 +48,13 @@ class ProblemData:
 
     # ---- norms of unscaled data (problemdata.jl:91-111)
     def get_normq(self):
+        if self.normq is None:                      # cleared by a data update: recover the unscaled norm
+            self.normq = float(np.abs(self.q * self.dinv).max()) / self.c if self.n else 0.0
         return self.normq
 
     def get_normb(self):
+        if self.normb is None:
+            self.normb = float(np.abs(self.b * self.einv).max()) if self.m else 0.0
         return self.normb
 
     def equilibrate(self, cones: CompositeCone, settings):

@@ -14,6 +14,7 @@ Timer sections use the reference's TimerOutputs names ("scale cones", "kkt updat
 """
 import time
 import numpy as np
+import scipy.sparse as sp
 
 from .settings import Settings
 from .cones import CompositeCone
@@ -120,6 +121,107 @@ class Solver:
         self.prev_vars = Variables(n, m)
         self.solution = Solution()
         self.timers["setup!"] = time.perf_counter() - t0
+
+    # ---------------------------------------------------------- data updates
+    # src/data_updating.jl:22-160: overwrite P / q / A / b in place (same sparsity pattern), scaled
+    # with the equilibration computed at setup, and push the new values to the KKT solver through
+    # kktsolver_update_P!/A! (no new symbolic analysis).  `data` may be None (no-op), a vector of
+    # the stored nonzeros / entries, a scipy matrix with the stored pattern, or an iterable of
+    # (index, value) pairs with 0-based indices into the stored values.
+    def _check_data_update_allowed(self):
+        if self.data.dropped_zeros:
+            raise RuntimeError("Data updates not allowed if sparse zeros are dropped.")
+
+    @staticmethod
+    def _pairs(data):
+        """list of (index, value) pairs if `data` is the zip / pair-sequence form, else None"""
+        if sp.issparse(data) or isinstance(data, np.ndarray):
+            return None
+        if hasattr(data, "__len__"):
+            seq = list(data)
+            if seq and isinstance(seq[0], (tuple, list)) and len(seq[0]) == 2:
+                return seq
+            return None
+        return list(data)
+
+    def _update_matrix(self, data, M, lscale, rscale, cscale):
+        if sp.issparse(data):
+            D = sp.csc_matrix(data, dtype=np.float64); D.sort_indices()
+            if (D.shape != M.shape or not np.array_equal(D.indptr, M.indptr)
+                    or not np.array_equal(D.indices, M.indices)):
+                raise ValueError("Input must match sparsity pattern of original data.")
+            data = D.data
+        cols = np.repeat(np.arange(M.shape[1]), np.diff(M.indptr))
+        pairs = self._pairs(data)
+        if pairs is not None:
+            for idx, value in pairs:
+                if not 0 <= idx < M.nnz:
+                    raise ValueError("Input must match sparsity pattern of original data.")
+                v = lscale[M.indices[idx]] * rscale[cols[idx]] * value
+                M.data[idx] = v if cscale is None else v * cscale
+            return True
+        data = np.asarray(data, dtype=np.float64)
+        if len(data) == 0:
+            return False
+        if len(data) != M.nnz:
+            raise ValueError("Input must match length of original data.")
+        M.data[:] = data * lscale[M.indices] * rscale[cols]
+        if cscale is not None:
+            M.data *= cscale
+        return True
+
+    @staticmethod
+    def _update_vector(data, v, vscale, cscale):
+        c = 1.0 if cscale is None else cscale
+        pairs = Solver._pairs(data)
+        if pairs is not None:
+            for idx, value in pairs:
+                v[idx] = value * vscale[idx] * c
+            return True
+        data = np.asarray(data, dtype=np.float64)
+        if len(data) == 0:
+            return False
+        if len(data) != len(v):
+            raise ValueError("Input must match length of original data.")
+        v[:] = data * vscale * c
+        return True
+
+    def update_P(self, data):
+        """update_P! (data_updating.jl:56-69); a matrix argument is the upper triangle of P."""
+        if data is None:
+            return
+        self._check_data_update_allowed()
+        d = self.data.d
+        if self._update_matrix(data, self.data.P, d, d, self.data.c):
+            self.kktsystem.update_P(self.data.P)
+
+    def update_A(self, data):
+        """update_A! (data_updating.jl:86-99)."""
+        if data is None:
+            return
+        self._check_data_update_allowed()
+        if self._update_matrix(data, self.data.A, self.data.e, self.data.d, None):
+            self.kktsystem.update_A(self.data.A)
+
+    def update_q(self, data):
+        """update_q! (data_updating.jl:108-122)."""
+        if data is None:
+            return
+        self._check_data_update_allowed()
+        if self._update_vector(data, self.data.q, self.data.d, self.data.c):
+            self.data.normq = None
+
+    def update_b(self, data):
+        """update_b! (data_updating.jl:131-144)."""
+        if data is None:
+            return
+        self._check_data_update_allowed()
+        if self._update_vector(data, self.data.b, self.data.e, None):
+            self.data.normb = None
+
+    def update_data(self, P=None, q=None, A=None, b=None):
+        """update_data! (data_updating.jl:22-37)."""
+        self.update_P(P); self.update_q(q); self.update_A(A); self.update_b(b)
 
     # ------------------------------------------------------------------ info
     def _info_update(self):

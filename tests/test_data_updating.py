@@ -1,0 +1,115 @@
+"""CPU: the data-update path of the caller (Solver.update_P/A/q/b -> kktsolver_update_P!/A!),
+scenario by scenario as test/OptTests/data_updating.jl (tolerance 1e-7 on the solutions of the
+updated solver vs a fresh solver on the new data).  Indices in the (index, value) form are 0-based
+here (the reference is 1-based)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+TOL = 1e-7
+
+
+def _data(cb):
+    P = sp.csc_matrix(np.array([[4.0, 1.0], [1.0, 2.0]]))
+    q = np.array([1.0, 1.0])
+    A0 = sp.identity(2, format="csc")
+    A = sp.vstack([-A0, A0]).tocsc()
+    b = np.array([1.0, 1.0, 1.0, 1.0])                       # [-l; u] with l = -1, u = 1
+    return P, q, A, b, [cb.NonnegativeConeT(2), cb.NonnegativeConeT(2)]
+
+
+def _fresh(cb, method, P, q, A, b, K):
+    return cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method=method)).solve()
+
+
+SCENARIOS = ["P_matrix", "P_vector", "P_pairs", "A_matrix", "A_vector", "A_pairs",
+             "q_vector", "q_pairs", "b_vector", "b_pairs", "all_at_once", "noop"]
+
+
+def run_scenario(cb, method, scenario):
+    P, q, A, b, K = _data(cb)
+    s1 = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method=method))
+    s1.solve()
+    P2, q2, A2, b2 = P.copy(), q.copy(), A.copy(), b.copy()
+    if scenario == "P_matrix":                               # data_updating.jl:34-57
+        P2 = sp.csc_matrix(np.array([[100.0, 1.0], [1.0, 2.0]]))
+        s1.update_P(sp.triu(P2).tocsc())
+    elif scenario == "P_vector":                             # :59-77
+        P2 = sp.csc_matrix(np.array([[100.0, 1.0], [1.0, 2.0]]))
+        s1.update_P(sp.triu(P2).tocsc().data)
+    elif scenario == "P_pairs":                              # :79-98 (1-based [2,3] -> 0-based [1,2])
+        s1.update_P(zip([1, 2], [3.0, 5.0]))
+        P2 = sp.csc_matrix(np.array([[4.0, 3.0], [0.0, 5.0]]))
+    elif scenario in ("A_matrix", "A_vector"):               # :100-146
+        A2 = A.tolil(); A2[1, 1] = -1000.0; A2 = A2.tocsc()
+        s1.update_A(A2 if scenario == "A_matrix" else A2.data)
+    elif scenario == "A_pairs":                              # :148-168
+        s1.update_A(zip([1, 2], [0.5, -0.5]))
+        A2 = A.copy(); A2.data[[1, 2]] = [0.5, -0.5]
+    elif scenario == "q_vector":                             # :170-190
+        q2[0] = 10.0; s1.update_q(q2)
+    elif scenario == "q_pairs":                              # :192-212
+        s1.update_q(zip([1], [10.0])); q2[1] = 10.0
+    elif scenario == "b_vector":                             # :214-234
+        b2[:] = 0.0; s1.update_b(b2)
+    elif scenario == "b_pairs":                              # :236-256
+        s1.update_b(zip([1, 3], [0.0, 0.0])); b2[[1, 3]] = 0.0
+    elif scenario == "all_at_once":                          # update_data! :22-37
+        P2 = sp.csc_matrix(np.array([[5.0, 0.5], [0.5, 3.0]])); q2 = np.array([-1.0, 2.0])
+        A2 = A.copy(); A2.data *= 1.5; b2 = b * 0.5
+        s1.update_data(sp.triu(P2).tocsc(), q2, A2, b2)
+    elif scenario == "noop":                                 # nothing / empty input: no action
+        s1.update_data(None, None, None, None); s1.update_P(np.zeros(0)); s1.update_b([])
+    sol1 = s1.solve()
+    sol2 = _fresh(cb, method, P2, q2, A2, b2, K)
+    assert sol1.status_name == sol2.status_name == "SOLVED"
+    assert np.linalg.norm(sol1.x - sol2.x) < TOL
+    assert abs(sol1.obj_val - sol2.obj_val) < 1e-6
+
+
+@pytest.mark.parametrize("scenario", SCENARIOS)
+def test_data_updating_oracle_backend(cb, scenario):
+    run_scenario(cb, "qdldl", scenario)
+
+
+def test_update_rejects_wrong_pattern_or_length(cb):
+    P, q, A, b, K = _data(cb)
+    s = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    with pytest.raises(ValueError):
+        s.update_P(np.ones(7))
+    with pytest.raises(ValueError):
+        s.update_A(sp.csc_matrix(np.ones((4, 2))))
+    with pytest.raises(ValueError):
+        s.update_q(np.ones(3))
+    with pytest.raises(ValueError):
+        s.update_P(zip([9], [1.0]))
+
+
+# ---------------------------------------------------------------- equilibration bounds
+# test/UnitTests/test_equilibration_bounds.jl:24-85 (the scaling decides the K values the path sees)
+def _equil_data(cb):
+    P = sp.csc_matrix(np.array([[4.0, 1.0], [1.0, 2.0]]))
+    c = np.array([1.0, 1.0])
+    A0 = sp.csc_matrix(np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]]))
+    A = sp.vstack([-A0, A0]).tolil()
+    b = np.array([-1.0, 0.0, 0.0, 1.0, 0.7, 0.7])
+    return P.tolil(), c, A, b, [cb.NonnegativeConeT(3), cb.NonnegativeConeT(3)]
+
+
+@pytest.mark.parametrize("case", ["lower", "upper", "zero_rows"])
+def test_equilibration_bounds(cb, case):
+    P, c, A, b, K = _equil_data(cb)
+    st = cb.Settings(direct_solve_method="qdldl")
+    if case == "lower":
+        P[0, 0] = 1e-15
+    elif case == "upper":
+        A[0, 0] = 1e15
+    else:
+        A = A.tocsc(); A.data[:] = 0.0
+    s = cb.Solver(sp.triu(P.tocsc()).tocsc(), c, A.tocsc(), b, K, st)
+    d, e = s.data.d, s.data.e
+    if case == "zero_rows":
+        assert np.all(e == 1.0)
+    else:
+        assert d.min() >= st.equilibrate_min_scaling and e.min() >= st.equilibrate_min_scaling
+        assert d.max() <= st.equilibrate_max_scaling and e.max() <= st.equilibrate_max_scaling
