@@ -2,8 +2,9 @@
 
 Decides the *values* of P, A the KKT matrix sees, so it must match the reference
 (src/problemdata.jl:3-88 constructor, :133-221 data_equilibrate!, src/utils/mathutils.jl
-kkt_col_norms!/scale_data!).  Presolve (inf-bound row removal) and chordal decomposition
-are out of scope: b is only capped at the reference's infinity.
+kkt_col_norms!/scale_data!).  The presolver (src/presolver.jl: rows of nonnegative cones whose
+bound is infinite are removed, the solution is padded back with s = infinity, z = 0) is mirrored
+because it changes the K the path sees; chordal decomposition is out of scope.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -29,9 +30,33 @@ class ProblemData:
         P = sp.csc_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=P.shape)
         P.sort_indices()
         A = _csc(A).copy()
+        b = np.array(b, dtype=np.float64)
+        # presolve (problemdata.jl:28-35, presolver.jl:107-147): only rows of NonnegativeCones
+        self.presolve_keep = None
+        self.mfull = len(b)
+        if settings.presolve_enable:
+            keep = np.ones(len(b), dtype=bool)
+            bound = INFINITY * (1 - 10 * np.finfo(np.float64).eps)
+            off = 0
+            new_cones = []
+            for c in cones:
+                k = c[1] if c[0] != "PSDTriangleConeT" else (c[1] * (c[1] + 1)) // 2
+                if c[0] == "NonnegativeConeT":
+                    keep[off:off + k] = ~(b[off:off + k] > bound)
+                    nkeep = int(keep[off:off + k].sum())
+                    if nkeep > 0:
+                        new_cones.append(("NonnegativeConeT", nkeep))
+                else:
+                    new_cones.append(c)
+                off += k
+            if not keep.all():
+                self.presolve_keep = keep
+                A = A[np.nonzero(keep)[0], :].tocsc(); A.sort_indices()
+                b = b[keep]
+                cones = new_cones
         self.P, self.A = P, A
         self.q = np.array(q, dtype=np.float64).copy()
-        self.b = np.minimum(np.array(b, dtype=np.float64), INFINITY)
+        self.b = np.minimum(b, INFINITY)
         self.cones = cones
         self.m, self.n = A.shape
         self.dropped_zeros = False

@@ -129,6 +129,8 @@ class Solver:
     # the stored nonzeros / entries, a scipy matrix with the stored pattern, or an iterable of
     # (index, value) pairs with 0-based indices into the stored values.
     def _check_data_update_allowed(self):
+        if self.data.presolve_keep is not None:
+            raise RuntimeError("Data updates not allowed if presolver is active.")
         if self.data.dropped_zeros:
             raise RuntimeError("Data updates not allowed if sparse zeros are dropped.")
 
@@ -490,6 +492,13 @@ class Solver:
         sol.x = v.x * data.d * scaleinv
         sol.z = v.z * data.e * (scaleinv * cinv)
         sol.s = v.s * data.einv * scaleinv
+        if data.presolve_keep is not None:
+            # reverse_presolve! (presolver.jl:82-104): removed rows get s = infinity, z = 0
+            from .problemdata import INFINITY
+            keep = data.presolve_keep
+            zf = np.zeros(data.mfull); sf = np.full(data.mfull, INFINITY)
+            zf[keep] = sol.z; sf[keep] = sol.s
+            sol.z, sol.s = zf, sf
         info.solve_time = time.perf_counter() - self._t_solve0
         sol.solve_time = info.solve_time
         sol.status_name = STATUS_NAMES[sol.status]

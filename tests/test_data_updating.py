@@ -113,3 +113,36 @@ def test_equilibration_bounds(cb, case):
     else:
         assert d.min() >= st.equilibrate_min_scaling and e.min() >= st.equilibrate_min_scaling
         assert d.max() <= st.equilibrate_max_scaling and e.max() <= st.equilibrate_max_scaling
+
+
+# ---------------------------------------------------------------- presolver (test/OptTests/presolve.jl)
+def _presolve_data(cb):
+    I3 = sp.identity(3, format="csc")
+    A = (sp.vstack([I3, -I3]) * 2.0).tocsc()
+    return I3.copy(), np.array([3.0, -2.0, 1.0]), A, np.ones(6), [cb.NonnegativeConeT(3), cb.NonnegativeConeT(3)]
+
+
+def test_presolver_single_unbounded_constraint(cb):
+    P, c, A, b, K = _presolve_data(cb)
+    b[3] = 1e30
+    s = cb.Solver(P, c, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    sol = s.solve()
+    assert sol.status_name == "SOLVED" and len(s.variables.z) == 5          # presolve.jl:34-44
+    assert sol.z[3] == 0.0 and sol.s[3] == 1e20 and len(sol.z) == 6
+    with pytest.raises(RuntimeError):
+        s.update_b(np.ones(6))                                             # data_updating.jl: not allowed when presolved
+
+
+def test_presolver_redundant_cone_and_all_redundant(cb):
+    P, c, A, b, K = _presolve_data(cb)
+    b[:3] = 1e30
+    s = cb.Solver(P, c, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    sol = s.solve()
+    assert sol.status_name == "SOLVED" and len(s.variables.z) == 3          # :46-60
+    assert np.all(sol.z[:3] == 0.0) and np.all(sol.s[:3] == 1e20)
+    assert np.linalg.norm(sol.x - np.array([-0.5, 2.0, -0.5])) < 1e-3
+    b[:] = 1e30
+    s = cb.Solver(P, c, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    sol = s.solve()
+    assert sol.status_name == "SOLVED" and len(s.variables.z) == 0          # :62-74
+    assert np.linalg.norm(sol.x + c) < 1e-3
