@@ -194,6 +194,30 @@ CONFIGS = {
 }
 
 
+def _cone_to_json(c):
+    """lower(cone) (src/json.jl:138-151)."""
+    if c[0] == "PowerConeT":
+        return {c[0]: c[2]}
+    if c[0] == "ExponentialConeT":
+        return {c[0]: []}
+    if c[0] == "GenPowerConeT":
+        return {c[0]: [list(c[2]), c[3]]}
+    return {c[0]: c[1]}
+
+
+def _cone_from_json(d):
+    """parse(dict, SupportedCone) (src/json.jl:196-216)."""
+    from . import cones as C
+    (key, val), = d.items()
+    if key == "GenPowerConeT":
+        return C.GenPowerConeT(val[0], int(val[1]))
+    if key == "ExponentialConeT":
+        return C.ExponentialConeT()
+    if key == "PowerConeT":
+        return C.PowerConeT(float(val))
+    return getattr(C, key)(int(val))
+
+
 def to_reference_json(path, P, q, A, b, cones, settings=None):
     """Write the instance in the reference's JSON schema (src/json.jl:118-156): CSC matrices as
     {m,n,colptr,rowval,nzval} with 0-based indices, cones as [{"NonnegativeConeT": k}, ...]."""
@@ -201,7 +225,20 @@ def to_reference_json(path, P, q, A, b, cones, settings=None):
         M = sp.csc_matrix(M); M.sort_indices()
         return dict(m=int(M.shape[0]), n=int(M.shape[1]), colptr=M.indptr.tolist(),
                     rowval=M.indices.tolist(), nzval=M.data.tolist())
-    doc = dict(P=mat(_triu(P)), q=np.asarray(q).tolist(), A=mat(A), b=np.asarray(b).tolist(),
-               cones=[{name: dim} for (name, dim) in cones], settings=settings or {})
+    doc = dict(settings=settings or {}, P=mat(_triu(P)), q=np.asarray(q, dtype=float).tolist(), A=mat(A),
+               b=np.asarray(b, dtype=float).tolist(), cones=[_cone_to_json(c) for c in cones])
     with open(path, "w") as f:
         json.dump(doc, f)
+
+
+def from_reference_json(path):
+    """Read a fixture written by the reference's `save_to_file` or by `to_reference_json`
+    (load_from_file, src/json.jl:58-80).  Returns (P, q, A, b, cones, settings_dict)."""
+    with open(path) as f:
+        doc = json.load(f)
+
+    def mat(d):
+        return sp.csc_matrix((np.asarray(d["nzval"], dtype=float), np.asarray(d["rowval"], dtype=np.int64),
+                              np.asarray(d["colptr"], dtype=np.int64)), shape=(int(d["m"]), int(d["n"])))
+    return (mat(doc["P"]), np.asarray(doc["q"], dtype=float), mat(doc["A"]), np.asarray(doc["b"], dtype=float),
+            [_cone_from_json(c) for c in doc["cones"]], dict(doc.get("settings") or {}))

@@ -122,6 +122,39 @@ class Solver:
         self.solution = Solution()
         self.timers["setup!"] = time.perf_counter() - t0
 
+    # ------------------------------------------------------------- fixtures
+    def save_to_file(self, path):
+        """save_to_file (src/json.jl:24-54): the problem as the solver holds it (after presolve),
+        in unscaled form, in the reference's JSON schema."""
+        import dataclasses
+        from .problems import to_reference_json
+        d = self.data
+        P = d.P.copy(); A = d.A.copy()
+        Pc = np.repeat(np.arange(d.n), np.diff(P.indptr)); Ac = np.repeat(np.arange(d.n), np.diff(A.indptr))
+        P.data *= d.dinv[P.indices] * d.dinv[Pc] / d.c
+        A.data *= d.einv[A.indices] * d.dinv[Ac]
+        st = {}
+        for k, v in dataclasses.asdict(self.settings).items():
+            if isinstance(v, float) and np.isinf(v):
+                v = float(np.sign(v) * np.finfo(np.float64).max)       # sanitize_settings!
+            st[k] = v
+        to_reference_json(path, P, d.q * d.dinv / d.c, A, d.b * d.einv, d.cones, st)
+
+    @classmethod
+    def load_from_file(cls, path, settings=None):
+        """load_from_file (src/json.jl:58-80); `settings` overrides the stored ones."""
+        from .problems import from_reference_json
+        P, q, A, b, cones, st = from_reference_json(path)
+        if settings is None:
+            settings = Settings()
+            fmax = float(np.finfo(np.float64).max)
+            for k, v in st.items():
+                if hasattr(settings, k):
+                    if isinstance(v, float) and abs(v) == fmax:
+                        v = float(np.sign(v) * np.inf)                  # desanitize_settings!
+                    setattr(settings, k, type(getattr(settings, k))(v))
+        return cls(P, q, A, b, cones, settings)
+
     # ---------------------------------------------------------- data updates
     # src/data_updating.jl:22-160: overwrite P / q / A / b in place (same sparsity pattern), scaled
     # with the equilibration computed at setup, and push the new values to the KKT solver through

@@ -146,3 +146,30 @@ def test_presolver_redundant_cone_and_all_redundant(cb):
     sol = s.solve()
     assert sol.status_name == "SOLVED" and len(s.variables.z) == 0          # :62-74
     assert np.linalg.norm(sol.x + c) < 1e-3
+
+
+# ---------------------------------------------------------------- JSON fixtures (test/UnitTests/test_json.jl)
+def test_json_roundtrip(cb, tmp_path):
+    P = sp.csc_matrix(np.array([[4.0, 1.0], [1.0, 2.0]]))
+    c = np.array([1.0, 1.0])
+    A = sp.csc_matrix(np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]]))
+    b = np.ones(3)
+    K = [cb.NonnegativeConeT(1), cb.ZeroConeT(1), cb.NonnegativeConeT(1)]
+    s1 = cb.Solver(P, c, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    f = str(tmp_path / "problem.json")
+    s1.save_to_file(f)
+    s2 = cb.Solver.load_from_file(f)
+    assert s2.settings.direct_solve_method == "qdldl"
+    x1, x2 = s1.solve(), s2.solve()
+    assert x1.status_name == x2.status_name and np.allclose(x1.x, x2.x, atol=1e-10)   # test_json.jl:24-25
+    st = cb.Settings(direct_solve_method="qdldl", max_iter=1)
+    s3 = cb.Solver.load_from_file(f, st)
+    assert s3.solve().status_name == "MAX_ITERATIONS"                                  # :29-33
+    # every cone type survives the schema (src/json.jl:138-151, 196-216)
+    from clarabel_jl_b200 import problems
+    K2 = [cb.ZeroConeT(1), cb.NonnegativeConeT(2), cb.SecondOrderConeT(3), cb.PSDTriangleConeT(2),
+          cb.ExponentialConeT(), cb.PowerConeT(0.3), cb.GenPowerConeT([0.25, 0.75], 2)]
+    m = sum(3 if k[0] == "PSDTriangleConeT" else k[1] for k in K2)
+    f2 = str(tmp_path / "cones.json")
+    problems.to_reference_json(f2, P, c, sp.csc_matrix((m, 2)), np.zeros(m), K2)
+    assert problems.from_reference_json(f2)[4] == K2

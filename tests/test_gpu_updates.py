@@ -2,7 +2,7 @@
 backend: Solver.update_P/A -> cb200_update_P/A, then a re-solve without a new symbolic analysis."""
 import pytest
 
-from test_data_updating import SCENARIOS, run_scenario
+from test_caller_paths import SCENARIOS, run_scenario
 
 pytestmark = pytest.mark.gpu
 
