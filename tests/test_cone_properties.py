@@ -99,3 +99,16 @@ def test_nn_and_composite_ranges(cb):
     col = cb.cones.cones_new_collapsed([cb.NonnegativeConeT(2), cb.SecondOrderConeT(1), cb.PSDTriangleConeT(1),
                                         cb.ZeroConeT(0), cb.NonnegativeConeT(3), cb.SecondOrderConeT(3)])
     assert col == [cb.NonnegativeConeT(7), cb.SecondOrderConeT(3)]
+
+
+def test_cones_new_collapsed_reference_cases(cb):
+    """test/UnitTests/test_cones_new_collapsed.jl, case by case."""
+    Z, NN, SOC, PSDT, EXP = cb.ZeroConeT, cb.NonnegativeConeT, cb.SecondOrderConeT, cb.PSDTriangleConeT, cb.ExponentialConeT
+    col = cb.cones.cones_new_collapsed
+    assert col([NN(3), SOC(4), EXP()]) == [NN(3), SOC(4), EXP()]                              # :3-13
+    assert col([NN(3), NN(2), SOC(4)]) == [NN(5), SOC(4)]                                     # :14-26
+    assert col([NN(3), Z(0), SOC(4), NN(0)]) == [NN(3), SOC(4)]                               # :27-40
+    assert col([SOC(1), SOC(4)]) == [NN(1), SOC(4)]                                           # :41-52
+    assert col([PSDT(1), SOC(4)]) == [NN(1), SOC(4)]                                          # :53-64
+    assert col([SOC(1), NN(3), NN(2), EXP(), NN(0), SOC(1)]) == [NN(6), EXP(), NN(1)]         # :65-81
+    assert col([NN(3), NN(2), Z(0), SOC(1), PSDT(1), SOC(4), NN(0)]) == [NN(7), SOC(4)]       # :82-98
