@@ -708,6 +708,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         }
         CUDA_OK(cudaSetDevice(st.device));
         auto* h = new cb200_handle();
+        struct Guard { cb200_handle* h; ~Guard() { if (h) cb200_destroy(h); } } guard{h};   // error paths free everything
         h->st = st; h->N = N; h->base = st.index_base;
         const int64_t base = st.index_base;
         std::vector<int64_t> cp(N + 1), ri;
@@ -769,7 +770,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
         // ---- level plans (+ workspace sized for them)
         h->use_panel_kernel = !(getenv("CB200_NO_PANEL") && getenv("CB200_NO_PANEL")[0] == '1');
-        { int rcp = build_plans(h); if (rcp) { delete h; return rcp; } }
+        { int rcp = build_plans(h); if (rcp) return rcp; }
         // ---- numeric storage
         CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
         CUDA_OK(h->d_U.alloc((size_t)std::max<int64_t>(1, S.upd_total)));
@@ -798,8 +799,9 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (GSM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); delete h; return -4; }
+        if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); return -4; }
         CUDA_OK(cudaStreamSynchronize(s));
+        guard.h = nullptr;
         *out = h;
         return 0;
     } catch (const std::exception& e) { set_error(e.what()); return -1; }
