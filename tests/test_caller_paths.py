@@ -26,7 +26,7 @@ SCENARIOS = ["P_matrix", "P_vector", "P_pairs", "A_matrix", "A_vector", "A_pairs
              "q_vector", "q_pairs", "b_vector", "b_pairs", "all_at_once", "noop"]
 
 
-def run_scenario(cb, method, scenario):
+def run_scenario(cb, method, scenario, tol=TOL):
     P, q, A, b, K = _data(cb)
     s1 = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method=method))
     s1.solve()
@@ -63,7 +63,7 @@ def run_scenario(cb, method, scenario):
     sol1 = s1.solve()
     sol2 = _fresh(cb, method, P2, q2, A2, b2, K)
     assert sol1.status_name == sol2.status_name == "SOLVED"
-    assert np.linalg.norm(sol1.x - sol2.x) < TOL
+    assert np.linalg.norm(sol1.x - sol2.x) < tol
     assert abs(sol1.obj_val - sol2.obj_val) < 1e-6
 
 
