@@ -429,7 +429,7 @@ def main():
                 e2e=dict(value=args.steps / (ms_e2e * 1e-3), unit="it/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 gpu_launches=int(tm["nlaunch"]), clocks=clocks_summary(samples), roofline=roofline)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N = 1 only
         rate, ms, sdesc, note = cpu_sample(name, 1, 1)
         line["cpu_baseline"] = scale_cpu_sample(name, rate, ms, sdesc, note, lambda: ks.KKT)[1]
     print(json.dumps(line))
