@@ -173,3 +173,14 @@ def test_json_roundtrip(cb, tmp_path):
     f2 = str(tmp_path / "cones.json")
     problems.to_reference_json(f2, P, c, sp.csc_matrix((m, 2)), np.zeros(m), K2)
     assert problems.from_reference_json(f2)[4] == K2
+
+
+def test_committed_c1_fixture_is_the_generated_instance(cb):
+    """tests/golden/C1.json (tools/export_fixtures.py) is BASELINE config C1 in the reference's own
+    fixture format; it must stay in sync with the generator the bench uses."""
+    import os
+    from clarabel_jl_b200 import problems
+    P, q, A, b, K, _ = problems.from_reference_json(os.path.join(os.path.dirname(__file__), "golden", "C1.json"))
+    P0, q0, A0, b0, K0 = problems.c1_random_qp()
+    assert K == list(K0) and np.array_equal(q, q0) and np.array_equal(b, b0)
+    assert (abs(sp.triu(P0) - P)).max() == 0 and (abs(sp.csc_matrix(A0) - A)).max() == 0
