@@ -53,10 +53,10 @@ static const int kPanelDoubles[NPANEL] = {4096, 9000, 16000, 1 << 30};   // smem
 constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
 
 // fronts handled by k_factor_panel: 64 < nf <= 152 (panel + scratch in one CTA's shared memory)
-inline bool panel_eligible(int nf, int ns) {
+inline bool panel_eligible(int nf, int ns, int min_nf = 64, int max_nf = 152) {
     // (measured: extending this to narrow fronts up to nf = 320 moves work from the pivot-block
     // kernels to 1-CTA-per-SM panels and is a net loss on C5, so the range stays 64 < nf <= 152)
-    return nf > 64 && nf <= 152 && ns <= 150 && ((int64_t)nf * ns + (int64_t)nf * 25) <= 27000;
+    return nf > min_nf && nf <= max_nf && ns <= 150 && ((int64_t)nf * ns + (int64_t)nf * 25) <= 27000;
 }
 
 struct LevelPlan {
@@ -202,6 +202,13 @@ struct cb200_handle {
     bool resident = false;
     int detail = 0;            // 1: per-phase event timing, 2: also per kernel class (both disable graph replay)
     bool use_panel_kernel = true;
+    // size-class boundaries of the factorisation plan (tuning knobs, environment variables
+    // CB200_PANEL_MIN_NF / CB200_PANEL_MAX_NF / CB200_SMALL_MAX_NF; defaults = measured best on C3/C5):
+    // panel kernel for panel_min_nf < nf <= panel_max_nf, shared-memory front kernel up to
+    // small_max_nf, pivot-block (large) path above
+    int panel_min_nf = 64, panel_max_nf = 152, small_max_nf = 152;
+    bool to_panel(int nf, int ns) const { return use_panel_kernel && panel_eligible(nf, ns, panel_min_nf, panel_max_nf); }
+    bool to_large(int nf, int ns) const { return nf > small_max_nf && !to_panel(nf, ns); }
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -417,7 +424,8 @@ int build_plans(cb200_handle* h) {
             }
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
-            if (h->use_panel_kernel && panel_eligible(nf, S.ns(sn))) {
+            if (nf > h->small_max_nf) c = NSMALL;
+            if (h->to_panel(nf, S.ns(sn))) {
                 int pc = 0; while (nf * S.ns(sn) + 25 * nf > kPanelDoubles[pc]) ++pc;
                 pcl[pc].push_back(sn);
             } else cls[c].push_back(sn);
@@ -770,6 +778,13 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
         // ---- level plans (+ workspace sized for them)
         h->use_panel_kernel = !(getenv("CB200_NO_PANEL") && getenv("CB200_NO_PANEL")[0] == '1');
+        auto env_int = [](const char* name, int dflt, int lo, int hi) {
+            const char* e = getenv(name);
+            return e ? std::max(lo, std::min(hi, atoi(e))) : dflt;
+        };
+        h->panel_min_nf = env_int("CB200_PANEL_MIN_NF", 64, 16, 152);
+        h->panel_max_nf = env_int("CB200_PANEL_MAX_NF", 152, 16, 152);
+        h->small_max_nf = env_int("CB200_SMALL_MAX_NF", 152, 16, 152);
         { int rcp = build_plans(h); if (rcp) return rcp; }
         // ---- numeric storage
         CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
@@ -1217,7 +1232,7 @@ int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
     double schur = 0, panel_large = 0, big_bytes = 0, nlarge = 0;
     for (int32_t sn = 0; sn < S.nsuper; ++sn) {
         const double ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
-        if (nf > kSmallNf[NSMALL - 1] && !(h->use_panel_kernel && panel_eligible((int)nf, (int)ns))) {
+        if (h->to_large((int)nf, (int)ns)) {
             nlarge += 1;
             schur += nr * (nr + 1.0) * ns;                 // flops of F22 -= L21 D L21' (lower part)
             for (double k = 0; k < ns; ++k) panel_large += (nf - k) * (nf - k);
