@@ -201,12 +201,8 @@ def test_b200_nonsymmetric_payload_equals_oracle_kkt_values(cb):
     assert (sp.tril(Kc, -1)).nnz == 0 and Kc.has_sorted_indices
 
 
-def test_mixed_symmetric_and_nonsymmetric_cones(cb):
-    """exp + SOC + PSD cones in one problem (unit initialisation, barrier, step-length and
-    ds-shift paths of every cone type together):
-        min  x3 + t + u   s.t.  x3 >= exp(x1),  t >= |(x1 - 1, 0.5)|,  [[u, x1], [x1, 1]] >= 0
-    whose value is min_x1 exp(x1) + sqrt((x1-1)^2 + 0.25) + x1^2."""
-    from scipy.optimize import minimize_scalar
+def _mixed_problem(cb):
+    """min x3 + t + u  s.t.  x3 >= exp(x1),  t >= |(x1 - 1, 0.5)|,  [[u, x1], [x1, 1]] >= 0"""
     r2 = np.sqrt(2.0)
     A = np.zeros((9, 4)); b = np.zeros(9)
     A[0, 0] = -1.0; b[1] = 1.0; A[2, 1] = -1.0                  # (x1, 1, x3) in K_exp
@@ -214,8 +210,15 @@ def test_mixed_symmetric_and_nonsymmetric_cones(cb):
     A[6, 3] = -1.0; A[7, 0] = -r2; b[8] = 1.0                   # svec [[u, x1], [x1, 1]] in PSD
     q = np.array([0.0, 1.0, 1.0, 1.0])
     K = [cb.ExponentialConeT(), cb.SecondOrderConeT(3), cb.PSDTriangleConeT(2)]
-    sol = cb.Solver(sp.csc_matrix((4, 4)), q, sp.csc_matrix(A), b, K,
-                    cb.Settings(direct_solve_method="qdldl")).solve()
+    return sp.csc_matrix((4, 4)), q, sp.csc_matrix(A), b, K
+
+
+def test_mixed_symmetric_and_nonsymmetric_cones(cb):
+    """exp + SOC + PSD cones in one problem (unit initialisation, barrier, step-length and
+    ds-shift paths of every cone type together); the optimal value is
+    min_x1 exp(x1) + sqrt((x1-1)^2 + 0.25) + x1^2."""
+    from scipy.optimize import minimize_scalar
+    sol = cb.Solver(*_mixed_problem(cb), cb.Settings(direct_solve_method="qdldl")).solve()
     f = lambda x: np.exp(x) + np.sqrt((x - 1) ** 2 + 0.25) + x * x
     ref = minimize_scalar(f, bounds=(-2, 2), method="bounded", options=dict(xatol=1e-12))
     assert sol.status_name == "SOLVED"
