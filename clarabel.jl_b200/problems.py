@@ -194,6 +194,35 @@ CONFIGS = {
 }
 
 
+def socp_lasso(nfeat=8, seed=12345):
+    """Lasso regression as an SOCP with the shape of the reference's test instance
+    (test/OptTests/socp-lasso.jl:6-56: 2*nfeat + 3 + m variables, rows NN(m + 2), NN(2 nfeat),
+    SOC(m + 2) with m = 50 nfeat).  The reference draws its data from Julia's MersenneTwister
+    stream, which cannot be reproduced here: same construction, numpy random data.
+        variables (t, v, u, w1, w2, y):  min t + mu sum(u) + |x|^2/2  (P = I as in the reference)"""
+    rng = np.random.default_rng(seed)
+    n = nfeat; m = 50 * n
+    F = rng.random((m, n))
+    vtrue = np.where(rng.random(n) < 0.1, rng.random(n), 0.0)
+    bb = F @ vtrue + 0.1 * rng.random(m)
+    mu = 0.1 * np.abs(F.T @ bb).max()
+    Z = np.zeros; I = np.eye
+    A1 = -np.block([[np.ones((1, 1)), Z((1, 2 * n + 1)), np.ones((1, 1)), Z((1, m))],
+                    [-np.ones((1, 1)), Z((1, 2 * n)), np.ones((1, 1)), Z((1, m + 1))],
+                    [Z((m, 1)), -2 * F, Z((m, n + 2)), I(m)]])
+    A2 = -np.block([[Z((n, 1)), I(n), -I(n), Z((n, m + 2))],
+                    [Z((n, 1)), -I(n), -I(n), Z((n, m + 2))]])
+    A3 = -np.block([[Z((1, 2 * n + 1)), -np.ones((1, 1)), Z((1, m + 1))],
+                    [Z((1, 2 * n + 2)), -np.ones((1, 1)), Z((1, m))],
+                    [Z((m, 2 * n + 3)), -I(m)]])
+    b = np.concatenate([[1.0, 1.0], -2 * bb, np.zeros(2 * n), np.zeros(m + 2)])
+    c = np.concatenate([[1.0], np.zeros(n), mu * np.ones(n), np.zeros(m + 2)])
+    P = sp.identity(len(c), format="csc")
+    A = sp.csc_matrix(np.vstack([A1, A2, A3]))
+    cones = [NonnegativeConeT(m + 2), NonnegativeConeT(2 * n), SecondOrderConeT(m + 2)]
+    return P, c, A, b, cones
+
+
 def _cone_to_json(c):
     """lower(cone) (src/json.jl:138-151)."""
     if c[0] == "PowerConeT":

@@ -184,3 +184,14 @@ def test_committed_c1_fixture_is_the_generated_instance(cb):
     P0, q0, A0, b0, K0 = problems.c1_random_qp()
     assert K == list(K0) and np.array_equal(q, q0) and np.array_equal(b, b0)
     assert (abs(sp.triu(P0) - P)).max() == 0 and (abs(sp.csc_matrix(A0) - A)).max() == 0
+
+
+def test_socp_lasso_shape_instance(cb):
+    """test/OptTests/socp-lasso.jl:58-65: 419 variables, 820 rows, a 402-dimensional second-order
+    cone (sparse expansion), status SOLVED."""
+    from clarabel_jl_b200 import problems
+    P, c, A, b, K = problems.socp_lasso()
+    assert A.shape == (820, 419) and [k[1] for k in K] == [402, 16, 402]
+    s = cb.Solver(P, c, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    assert s.cones.p == 2                                       # NN cones collapse, one expanded SOC
+    assert s.solve().status_name == "SOLVED"

@@ -21,3 +21,12 @@ def test_nonsymmetric_problems_match_the_oracle(cb, make):
     assert abs(sg.obj_val - so.obj_val) <= 1e-6 * max(1.0, abs(so.obj_val))
     assert np.allclose(sg.x, so.x, rtol=1e-5, atol=1e-5)
     assert sg_solver.kktsystem.kktsolver.ldl.timers()["nlaunch"] > 0
+
+
+def test_lasso_shape_instance_matches_the_oracle(cb):
+    """test/OptTests/socp-lasso.jl shape (one 402-dimensional expanded SOC) through the B200 backend."""
+    from clarabel_jl_b200 import problems
+    so = cb.Solver(*problems.socp_lasso(), cb.Settings(direct_solve_method="qdldl")).solve()
+    sg = cb.Solver(*problems.socp_lasso(), cb.Settings(direct_solve_method="b200")).solve()
+    assert sg.status_name == so.status_name == "SOLVED" and sg.iterations == so.iterations
+    assert abs(sg.obj_val - so.obj_val) <= 1e-6 * max(1.0, abs(so.obj_val))
