@@ -4,12 +4,13 @@ are host-computed and reach the device through update_values! (INTEGRATION.md); 
 import numpy as np
 import pytest
 
-from test_nonsymmetric_cones import _exp_problem, _pow_problem, _genpow_problem, _mixed_problem
+from test_nonsymmetric_cones import (_exp_problem, _pow_problem, _genpow_problem, _mixed_problem,
+                                      _sdp_chordal_problem)
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("make", [_exp_problem, _pow_problem, _genpow_problem, _mixed_problem])
+@pytest.mark.parametrize("make", [_exp_problem, _pow_problem, _genpow_problem, _mixed_problem, _sdp_chordal_problem])
 def test_nonsymmetric_problems_match_the_oracle(cb, make):
     so = cb.Solver(*make(cb), cb.Settings(direct_solve_method="qdldl")).solve()
     sg_solver = cb.Solver(*make(cb), cb.Settings(direct_solve_method="b200"))

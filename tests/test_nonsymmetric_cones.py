@@ -223,3 +223,23 @@ def test_mixed_symmetric_and_nonsymmetric_cones(cb):
     ref = minimize_scalar(f, bounds=(-2, 2), method="bounded", options=dict(xatol=1e-12))
     assert sol.status_name == "SOLVED"
     assert abs(sol.obj_val - ref.fun) < 1e-6 and abs(sol.x[0] - ref.x) < 1e-4
+
+
+def _sdp_chordal_problem(cb):
+    """The explicit CSC instance of test/OptTests/sdp_chordal.jl:6-76 (NN(1), PSD(6), Pow(1/3),
+    Pow(1/2)); the reference solves it under every chordal-decomposition setting, which is an
+    equivalent reformulation -- here it is solved undecomposed (decomposition is out of scope)."""
+    r2 = np.sqrt(2.0)
+    colptr = np.array([0, 1, 4, 5, 8, 9, 10, 13, 16])
+    rowval = np.array([24, 7, 10, 22, 8, 12, 15, 25, 9, 13, 18, 21, 26, 0, 23, 27])
+    nzval = np.array([-1.0, -r2, -1.0, -1.0, -r2, -r2, -1.0, -1.0, -r2, -r2, -r2, -1.0, -1.0, -1.0, -1.0, -1.0])
+    A = sp.csc_matrix((nzval, rowval, colptr), shape=(28, 8))
+    b = np.zeros(28); b[1:7] = [3.0, 2 * r2, 2.0, r2, r2, 3.0]
+    c = np.zeros(8); c[0] = -1.0
+    K = [cb.NonnegativeConeT(1), cb.PSDTriangleConeT(6), cb.PowerConeT(0.3333333333333333), cb.PowerConeT(0.5)]
+    return sp.csc_matrix((8, 8)), c, A, b, K
+
+
+def test_reference_sdp_chordal_instance_undecomposed(cb):
+    sol = cb.Solver(*_sdp_chordal_problem(cb), cb.Settings(direct_solve_method="qdldl")).solve()
+    assert sol.status_name == "SOLVED"                              # sdp_chordal.jl:101
