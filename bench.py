@@ -430,8 +430,12 @@ def main():
                          h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 gpu_launches=int(tm["nlaunch"]), clocks=clocks_summary(samples), roofline=roofline)
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N = 1 only
-        rate, ms, sdesc, note = cpu_sample(name, 1, 1)
-        line["cpu_baseline"] = scale_cpu_sample(name, rate, ms, sdesc, note, lambda: ks.KKT)[1]
+        try:
+            rate, ms, sdesc, note = cpu_sample(name, 1, 1)
+            line["cpu_baseline"] = scale_cpu_sample(name, rate, ms, sdesc, note, lambda: ks.KKT)[1]
+        except Exception as e:                      # the GPU measurement above must still be reported
+            line["cpu_baseline"] = dict(value=None, unit="it/s", cores=1, kind="port",
+                                        sample=f"CPU leg failed: {type(e).__name__}: {e}")
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
