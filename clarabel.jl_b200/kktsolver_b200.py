@@ -16,6 +16,7 @@ update_values!/scale_values!/refactor!/solve! exactly as it drives QDLDL.
 """
 import ctypes as C
 import os
+import sys
 import numpy as np
 
 from . import lib as _lib
@@ -189,12 +190,12 @@ class B200KKTSolver:
         self.ldl = B200DirectLDLSolver(self.KKT, self.Dsigns, settings, **cs_over)
         # one process per GPU: if the caller runs under torch.distributed, shard the elimination
         # tree over the ranks (every rank must then make the same calls with the same inputs)
-        try:
+        # (a process group can only be initialised if torch is already imported: do not pay the
+        # torch import in single-GPU callers)
+        if "torch" in sys.modules:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 dist_init_from_torch(self.ldl)
-        except ImportError:
-            pass
         L, h = self.ldl._L, self.ldl._h
         mp = self.map
         ctype = np.ascontiguousarray(cones.types, dtype=np.int32)
