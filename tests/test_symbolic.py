@@ -3,6 +3,7 @@ sets) checked by running a numpy emulation of the multifrontal numeric phase on 
 comparing with the QDLDL oracle and scipy's SuperLU; plus the C-ABI export check."""
 import ctypes
 import numpy as np
+import scipy.sparse as sp
 import scipy.sparse.linalg as spl
 import pytest
 from common import small_instances, kkt_fixture, sym_full
@@ -135,3 +136,39 @@ def test_nd_result_independent_of_host_threads(monkeypatch):
     S_nd = lib.Symbolic(K, ordering=1, nd_leaf=64).stats
     S_nat = lib.Symbolic(K, ordering=2).stats
     assert S_nd["nnzL"] < 0.5 * S_nat["nnzL"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_symbolic_maps_on_random_quasidefinite_patterns(seed):
+    """Randomised structures the instance generators do not produce: empty P, empty rows/columns of
+    A, disconnected blocks, dense rows/columns, tiny and degenerate sizes; both orderings.  The
+    numpy multifrontal runs on exactly the maps the CUDA kernels consume."""
+    from clarabel_jl_b200 import lib
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 60)); m = int(rng.integers(0, 80))
+    dens = float(rng.choice([0.02, 0.1, 0.4]))
+    rs = np.random.RandomState(seed)
+    Ph = sp.random(n, n, dens, random_state=rs)
+    P = (Ph @ Ph.T + sp.identity(n) * (0.5 if seed % 3 else 1.0)).tocsc() if seed % 5 else sp.identity(n, format="csc")
+    A = sp.random(m, n, dens, random_state=rs).tolil()
+    if m > 3 and n > 3:
+        A[0, :] = 1.0 if seed % 2 else 0.0                      # dense or empty row
+        A[:, 0] = 0.0                                           # empty column
+        if seed % 4 == 0:
+            A[m // 2:, : n // 2] = 0.0; A[: m // 2, n // 2:] = 0.0      # two disconnected blocks
+    A = A.tocsc()
+    K = sp.bmat([[P, A.T], [A, -sp.identity(m) * 0.7]]).tocsc() if m else P
+    K = sp.triu(K).tocsc(); K.sort_indices()
+    N = n + m
+    Ds = np.r_[np.ones(n, dtype=np.int64), -np.ones(m, dtype=np.int64)]
+    Kf = sym_full(K)
+    b = rng.standard_normal(N)
+    xs = np.linalg.solve(Kf.toarray(), b)
+    for ordering in (0, 1, 2):
+        a = lib.Symbolic(K, ordering=ordering, nd_leaf=8).arrays()
+        assert sorted(a["perm"].tolist()) == list(range(N))
+        mf = MFNumpy(a)
+        D = mf.factor(K.data, Ds)
+        assert np.all(np.sign(D) == Ds[a["perm"]]) and mf.nreg == 0
+        x = mf.solve(b)
+        assert np.abs(x - xs).max() < 1e-8 * max(1.0, np.abs(xs).max())
