@@ -142,7 +142,7 @@ def test_partition_covers_tree_and_balances(cb):
             assert top.sum() >= 1 and load.max() <= 0.75 * load.sum() + 1e-9
 
 
-@pytest.mark.parametrize("name,world", [("C5s", 2), ("C3s", 2), ("C1s", 2), ("C3s", 4), ("C5s", 4)])
+@pytest.mark.parametrize("name,world", [("C5s", 2), ("C3s", 2), ("C1s", 2), ("C3s", 4), ("C5s", 4), ("C5s", 8)])
 def test_distributed_multifrontal_gloo(cb, name, world):
     port = _free_port()
     ctx = mp.get_context("spawn")
