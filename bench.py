@@ -6,19 +6,30 @@ AbstractKKTSolver boundary exactly as `solve!` issues it (src/solver.jl:278-323)
     kktsolver_update!(cones)                    value scatter + static reg + numeric LDL'
     3 x (kktsolver_setrhs! ; kktsolver_solve!)  constant-RHS, affine and combined solves, each
                                                 with iterative refinement
-on cone states / right-hand sides recorded from a real IP run of the synthetic instance.
+on cone states / right-hand sides recorded from a COMPLETE interior-point solve of the synthetic
+instance on the GPU backend (the replayed set mixes the first, a middle and the last two iterates,
+so the late, badly scaled systems are timed and checked too).
 
   value : steps/s with the recorded inputs already resident in HBM (cb200_set_resident)
   e2e   : steps/s through the C-ABI with HOST buffers (H2D of the cone state and the three
           right-hand sides and D2H of the three solutions inside the timed region)
-Timing: CUDA events on the library's own stream, max over ranks, W warm-up steps first.  The
+  parity: after the timed region the last recorded system is solved once more; reported are the
+          relative residual against the UNREGULARISED K (host SpMV, independent of the factor),
+          IR rounds, dynamically regularised pivots and, when the CPU leg ran, the relative
+          difference to the CPU QDLDL-path solution of the same three right-hand sides
+  cpu_baseline : the CPU oracle (QDLDL-algorithm restatement, 1 thread like
+          directldl_qdldl.jl:37) on the SAME full-size instance and the same recorded system:
+          one full step, timed; no extrapolation.  It runs after the GPU line has been printed
+          (and flushed) once, under a wall-clock limit; the completed line is printed last.
+Timing: CUDA events on the library's own stream, max over ranks, W >= 3 warm-up steps.  The
 factor/solve working set (panel storage) is far larger than the 126 MB L2 for every workload
 except C1, so no explicit L2 flush is done ("inputs larger than L2").
 
---impl reference : the reference's CPU path (QDLDL-algorithm restatement, 1 thread like
-directldl_qdldl.jl:37) on a bounded sample of the same workload; the measured sample rate is
-converted to iterations of the FULL workload per second with the per-step flop ratio
-(scale_cpu_sample), the raw rate stays in cpu_baseline.sample_value.
+--impl reference : the reference's CPU path on the SAME full-size instance (no sampling, no flop
+ratio): the oracle runs the real interior-point iterations and the KKT sections of the first
+iterations are timed.  When a single step costs more than the time budget allows (C5: ~2.5 min
+per factorisation), the one step that is timed is the solver's own first factorisation
+(solver_default_start!, identity scaling) + 3 solves; `steps` in the line says how many were timed.
 """
 import argparse
 import json
@@ -33,71 +44,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "IP-iterations/sec (KKT assemble+factor+solve)"
+
 WORKLOADS = {
-    # name: (generator kwargs for the GPU arm, kwargs for the bounded CPU sample, sample note)
-    "C1": ("c1_random_qp", {}, {}, "full C1 instance"),
-    "C2": ("c2_portfolio", {}, {"n": 20000}, "same generator at n=2e4 (1/5 of the assets)"),
-    "C3": ("c3_socp", {}, {"n": 100000, "ncones": 2000}, "same generator at n=1e5, 2000 cones (1/5)"),
-    "C4": ("c4_sdp", {}, {"ncones": 20, "side": 30, "n": 3000, "vars_per_cone": 200},
-           "same generator, 20 cones of side 30"),
-    "C4r": ("c4_sdp", {"ncones": 40, "side": 40, "n": 8000, "vars_per_cone": 300},
-            {"ncones": 20, "side": 30, "n": 3000, "vars_per_cone": 200},
-            "reduced C4 (40 PSD cones of side 40); CPU sample: 20 cones of side 30"),
-    "C5": ("c5_block_angular", {}, {"nblocks": 2, "nlink": 64},
-           "2 of the 64 diagonal blocks with proportionally fewer linking rows (same generator, "
-           "nblocks=2, nlink=64): 1/32 of the full instance; CPU time per iteration grows at least "
-           "linearly in the number of blocks"),
+    # name: (generator, kwargs).  C1..C5 are the BASELINE.json configs at their stated sizes;
+    # C4r is a reduced SDP kept for development runs.
+    "C1": ("c1_random_qp", {}),
+    "C2": ("c2_portfolio", {}),
+    "C3": ("c3_socp", {}),
+    "C4": ("c4_sdp", {}),
+    "C4r": ("c4_sdp", {"ncones": 40, "side": 40, "n": 8000, "vars_per_cone": 300}),
+    "C5": ("c5_block_angular", {}),
 }
+ORDERING_NAMES = {0: "amd", 1: "nested-dissection", 2: "natural", 3: "user"}
+CPU_LEG_LIMIT_S = float(os.environ.get("CB200_CPU_LEG_LIMIT", "330"))      # wall clock, b200 arm
+REF_ARM_BUDGET_S = float(os.environ.get("CB200_REF_BUDGET", "200"))        # timed CPU work, reference arm
 
 
-def describe(name, P, A, ks):
-    info = ks.ldl.info() if hasattr(ks, "ldl") and hasattr(ks.ldl, "info") else None
-    return dict(workload=name, n=int(A.shape[1]), m=int(A.shape[0]), N=int(ks.KKT.shape[0]),
-                nnzK=int(ks.KKT.nnz), nnzL=int(info.nnzL) if info else int(ks.ldl.nnzL))
+def make_problem(name):
+    from clarabel_jl_b200 import problems
+    gen, kw = WORKLOADS[name]
+    return getattr(problems, gen)(**kw)
 
 
-REPLAY_ITERS = 2      # IP iterations run to record realistic cone states / right-hand sides
-SOLVES_PER_STEP = 6.0  # 3 right-hand sides, each with one refinement round (observed on C1..C5)
-
-
-def kkt_step_work(factor_flops, nnzL, N):
-    """Algorithmic flops of one step: numeric LDL' = sum_j l_j^2, plus
-    SOLVES_PER_STEP triangular solves of 4 nnzL + N each."""
-    return float(factor_flops) + SOLVES_PER_STEP * (4.0 * float(nnzL) + float(N))
-
-
-def full_size_work(KKT):
-    """Work of one step on the full workload under the CPU path's AMD-class ordering (host-only
-    symbolic analysis of this repo's library; no numerics)."""
-    from clarabel_jl_b200 import lib as cblib
-    st = cblib.Symbolic(KKT, ordering=0).stats
-    return kkt_step_work(st["flops"], st["nnzL"], st["N"]), dict(N=int(st["N"]), nnzL=int(st["nnzL"]), factor_flops=float(st["flops"]))
-
-
-def scale_cpu_sample(name, rate, ms, sdesc, note, full_KKT_fn):
-    """The CPU arm runs a bounded sample; its rate is converted to the metric's unit (iterations
-    of the FULL workload per second) by the ratio of algorithmic work per step.  This assumes the
-    scalar CPU code keeps its sample flop rate on the 30-100x larger factor (optimistic for the CPU:
-    the sample's L fits in cache, the full one does not)."""
-    gen, kw, skw, _ = WORKLOADS[name]
-    w_s = kkt_step_work(sdesc["factor_flops"], sdesc["nnzL"], sdesc["N"])
-    if kw == skw:
-        return rate, dict(value=rate, unit="it/s", cores=1, kind="port", sample=note, sample_config=sdesc,
-                          sample_value=rate, sample_ms_per_step=ms, work_ratio=1.0)
-    w_f, fdesc = full_size_work(full_KKT_fn())
-    ratio = w_s / w_f
-    cb_ = dict(value=rate * ratio, unit="it/s", cores=1, kind="port",
-               sample=note + "; value = measured sample rate x (flops of one sample step / flops of one "
-               "full-size step), flops = sum_j l_j^2 + 6 (4 nnzL + N) under the AMD-class ordering",
-               sample_config=sdesc, sample_value=rate, sample_ms_per_step=ms, work_ratio=ratio,
-               full_size=fdesc)
-    return rate * ratio, cb_
+def workload_config(name, data, N, nnzK):
+    """Identical in both arms: what the instance is, nothing about how an arm solves it."""
+    gen, kw = WORKLOADS[name]
+    return dict(workload=name, generator=gen, generator_kwargs=kw, n=int(data.n), m=int(data.m),
+                N=int(N), nnzK=int(nnzK), l2="inputs larger than L2 (no flush)")
 
 
 class Recorder:
     """Wraps a KKT solver and records the inputs of every boundary call of an IP run."""
-    def __init__(self, ks, cones):
-        self.ks, self.cones = ks, cones
+    def __init__(self, ks):
+        self.ks = ks
         self.steps = []          # list of dict(state=..., rhs=[(rx, rz), ...])
         self._u, self._s, self._r = ks.update, ks.solve, ks.setrhs
         ks.update, ks.solve, ks.setrhs = self.update, self.solve, self.setrhs
@@ -127,6 +107,32 @@ class FakeCones:
 
     def export_state(self):
         return self.st
+
+
+def apply_state_to_oracle_cones(cones, st):
+    """Overwrite the scaling state of a CompositeCone with a recorded one (CPU oracle replay)."""
+    cones.w[:] = st["w"]; cones.soc_eta[:] = st["soc_eta"]; cones.soc_d[:] = st["soc_d"]
+    cones.soc_u[:] = st["soc_u"]; cones.soc_v[:] = st["soc_v"]
+    if len(st["psd_R"]):
+        off = 0
+        pos = {}
+        for g in cones.psd_groups:
+            for j, ci in enumerate(g["cones"]):
+                pos[ci] = (g, j)
+        for ci in [i for i, t in enumerate(cones.types) if t == 3]:
+            g, j = pos[ci]; n = g["n"]
+            g["R"][j] = st["psd_R"][off:off + n * n].reshape(n, n, order="F"); off += n * n
+    return cones
+
+
+def pick_replay(steps):
+    """first / middle / last two complete IP iterations (each with its 3 right-hand sides)."""
+    full = [(i, s) for i, s in enumerate(steps) if len(s["rhs"]) == 3]
+    if not full:
+        return [(len(steps) - 1, steps[-1])]
+    k = len(full)
+    idx = sorted(set([0, k // 2, max(0, k - 2), k - 1]))
+    return [full[i] for i in idx]
 
 
 def sample_clocks(stop, out):
@@ -159,57 +165,131 @@ def clocks_summary(samples):
                 reasons=sorted(reasons))
 
 
-def cpu_sample(name, steps, warmup):
-    """Times the CPU oracle (QDLDL-algorithm restatement, 1 thread) on the bounded sample."""
+def sym_matvec(K):
+    """x -> K x for the symmetric matrix stored as upper-triangular scipy CSC."""
+    import scipy.sparse as sp
+    Ku = sp.triu(K, 1).tocsr()
+    Kt = K.T.tocsr()
+    return lambda x: Kt @ x + Ku @ x
+
+
+# --------------------------------------------------------------------------------------------
+# CPU oracle legs (the ONLY places bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------
+def oracle_solver(problem):
     import clarabel_jl_b200 as cb
-    from clarabel_jl_b200 import problems
     from oracle.kktsolver_oracle import OracleDirectLDLKKTSolver
     cb.register_kktsolver("qdldl", OracleDirectLDLKKTSolver)
-    gen, _, skw, note = WORKLOADS[name]
-    P, q, A, b, K = getattr(problems, gen)(**skw)
-    s = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="qdldl"))
-    ks = s.kktsystem.kktsolver
-    rec = Recorder(ks, s.cones)
-    s.solve(max_iter=REPLAY_ITERS)
-    rec.detach()
-    replay = [st for st in rec.steps[1:] if len(st["rhs"]) == 3] or rec.steps[-1:]
-    lx, lz = np.zeros(s.data.n), np.zeros(s.data.m)
-
-    def step(i):
-        st = replay[i % len(replay)]
-        ok = ks.update(FakeOracleCones(s.cones, st["state"]))
-        for rx, rz in st["rhs"]:
-            ks.setrhs(rx, rz); ok &= ks.solve(lx, lz)
-        return ok
-    for i in range(warmup):
-        step(i)
+    P, q, A, b, K = problem
     t0 = time.perf_counter()
-    for i in range(steps):
-        step(warmup + i)
-    dt = time.perf_counter() - t0
-    desc = describe(name + "-sample", P, A, ks)
-    desc["factor_flops"] = float(ks.ldl.sum_lnz_sq)
-    return steps / dt, dt / steps * 1e3, desc, note
+    s = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="qdldl"))
+    return s, time.perf_counter() - t0
 
 
-class FakeOracleCones:
-    """A CompositeCone whose scaling state is overwritten by a recorded one (CPU oracle replay)."""
-    def __new__(cls, cones, st):
-        cones.w[:] = st["w"]; cones.soc_eta[:] = st["soc_eta"]; cones.soc_d[:] = st["soc_d"]
-        cones.soc_u[:] = st["soc_u"]; cones.soc_v[:] = st["soc_v"]
-        off = 0
-        psd = [i for i, t in enumerate(cones.types) if t == 3]
-        for g in cones.psd_groups:
-            pass
-        if len(st["psd_R"]):
-            pos = {}
-            for g in cones.psd_groups:
-                for j, ci in enumerate(g["cones"]):
-                    pos[ci] = (g, j)
-            for ci in psd:
-                g, j = pos[ci]; n = g["n"]
-                g["R"][j] = st["psd_R"][off:off + n * n].reshape(n, n, order="F"); off += n * n
-        return cones
+def cpu_full_step(problem, step, out):
+    """One full-size step of the CPU QDLDL path on a recorded system; fills `out` (runs in a thread)."""
+    try:
+        s, t_setup = oracle_solver(problem)
+        ks = s.kktsystem.kktsolver
+        n, m = s.data.n, s.data.m
+        apply_state_to_oracle_cones(s.cones, step["state"])
+        sols = []
+        t0 = time.perf_counter()
+        ok = ks.update(s.cones)
+        t_fac = time.perf_counter() - t0
+        for rx, rz in step["rhs"]:
+            lx, lz = np.zeros(n), np.zeros(m)
+            ks.setrhs(rx, rz); ok &= bool(ks.solve(lx, lz))
+            sols.append(np.concatenate([lx, lz]))
+        dt = time.perf_counter() - t0
+        out.update(ok=bool(ok), seconds=dt, factor_seconds=t_fac, setup_seconds=t_setup, sols=sols,
+                   nnzL=int(ks.ldl.nnzL), factor_flops=float(ks.ldl.sum_lnz_sq))
+    except Exception as e:                                   # reported, never fatal for the GPU line
+        out.update(error=f"{type(e).__name__}: {e}")
+
+
+class _BudgetExhausted(Exception):
+    pass
+
+
+def reference_arm(name, steps, warmup):
+    """The reference's CPU path on the full-size instance: real IP iterations, KKT sections timed."""
+    problem = make_problem(name)
+    s, t_setup = oracle_solver(problem)
+    ks = s.kktsystem.kktsolver
+    n, m = s.data.n, s.data.m
+    u0, s0, r0 = ks.update, ks.solve, ks.setrhs
+    acc = dict(t=0.0, updates=0, per_iter=[], cur=0.0, last_rhs=None, nsolve=0)
+    want_warm = min(max(0, warmup), 1)
+
+    def upd(cones):
+        # an update opens a new step; the previous one (if any) is complete
+        if acc["updates"] > 0:
+            acc["per_iter"].append((acc["cur"], acc["nsolve"]))
+        timed_done = len(acc["per_iter"]) - 1 - want_warm       # entry 0 is solver_default_start!
+        spent = sum(t for t, _ in acc["per_iter"][1 + want_warm:])
+        nxt = acc["per_iter"][-1][0] if acc["per_iter"] else 0.0
+        if acc["per_iter"] and (timed_done >= steps or spent + nxt > REF_ARM_BUDGET_S
+                                or (timed_done < 0 and acc["per_iter"][0][0] > REF_ARM_BUDGET_S / 3)):
+            raise _BudgetExhausted()
+        acc["updates"] += 1; acc["cur"] = 0.0; acc["nsolve"] = 0
+        t = time.perf_counter(); r = u0(cones); acc["cur"] += time.perf_counter() - t
+        return r
+
+    def setrhs(rx, rz):
+        acc["last_rhs"] = (np.array(rx, copy=True), np.array(rz, copy=True))
+        t = time.perf_counter(); r = r0(rx, rz); acc["cur"] += time.perf_counter() - t
+        return r
+
+    def sol(lx, lz):
+        t = time.perf_counter(); r = s0(lx, lz); acc["cur"] += time.perf_counter() - t
+        acc["nsolve"] += 1
+        return r
+    ks.update, ks.solve, ks.setrhs = upd, sol, setrhs
+    status = None
+    try:
+        res = s.solve(max_iter=want_warm + steps + 1)
+        status = res.status_name
+        if acc["updates"] > len(acc["per_iter"]):
+            acc["per_iter"].append((acc["cur"], acc["nsolve"]))
+    except _BudgetExhausted:
+        pass
+    ks.update, ks.solve, ks.setrhs = u0, s0, r0
+    per = acc["per_iter"]
+    timed = per[1 + want_warm:1 + want_warm + steps]
+    timed = [t for t in timed if t[1] >= 3]
+    if timed:
+        what = (f"IP iterations {1 + want_warm}..{want_warm + len(timed)} of the full-size solve "
+                f"(update + 3 solves each), after solver_default_start! and {want_warm} untimed iteration(s)")
+        tt = [t for t, _ in timed]
+    else:
+        # a single step is all the budget allows: solver_default_start!'s factorisation (identity
+        # scaling) + its solves, completed to 3 solves with the same right-hand side
+        t_extra = 0.0
+        nso = per[0][1]
+        lx, lz = np.zeros(n), np.zeros(m)
+        while nso < 3:
+            t = time.perf_counter(); r0(*acc["last_rhs"]); s0(lx, lz); t_extra += time.perf_counter() - t
+            nso += 1
+        tt = [per[0][0] + t_extra]
+        what = ("1 step = solver_default_start!'s factorisation (identity scaling) + 3 solves; one such "
+                f"step takes {tt[0]:.0f} s on this instance, more would exceed the time budget")
+    dt = float(np.sum(tt))
+    v = len(tt) / dt
+    N = s.kktsystem.kktsolver.KKT.shape[0]
+    line = dict(metric=METRIC, value=v, unit="it/s", n_gpus=1, steps=len(tt), warmup=want_warm if timed else 0,
+                ms_per_step=1e3 / v, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=workload_config(name, s.data, N, ks.KKT.nnz),
+                cpu_baseline=dict(value=v, unit="it/s", cores=1, kind="port",
+                                  sample="FULL-SIZE instance, " + what,
+                                  engine="oracle/qdldl_oracle.c (QDLDL algorithm, 1 thread like "
+                                         "directldl_qdldl.jl:37), AMD-class ordering with the reference's "
+                                         "amd_dense_scale = 1.5",
+                                  nnzL=int(ks.ldl.nnzL), factor_flops=float(ks.ldl.sum_lnz_sq),
+                                  setup_seconds=t_setup, step_seconds=tt, status_after=status),
+                e2e=dict(value=v, unit="it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    return line
 
 
 def _watchdog(seconds):
@@ -218,46 +298,37 @@ def _watchdog(seconds):
     faulthandler.dump_traceback_later(seconds, exit=True)
 
 
+def load_traffic(name):
+    """ncu dram__bytes of the kernel classes (per call), committed under profiles/ (see
+    profiles/r02_summary.md for the command); None when no capture exists for the workload."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(name)
+    except Exception:
+        return None
+
+
 def main():
-    _watchdog(int(os.environ.get("CB200_BENCH_TIMEOUT", "840")))
+    _watchdog(int(os.environ.get("CB200_BENCH_TIMEOUT", "1500")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CB200_WORKLOAD", "C5"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
-    metric = "IP-iterations/sec (KKT assemble+factor+solve)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        rate, ms, desc, note = cpu_sample(name, max(1, args.steps), max(0, min(args.warmup, 1)))
-
-        def full_kkt():
-            import clarabel_jl_b200 as cb
-            from clarabel_jl_b200 import problems, kkt_assembly as ka
-            gen, kw, _, _ = WORKLOADS[name]
-            P, q, A, b, K = getattr(problems, gen)(**kw)
-            data = cb.problemdata.ProblemData(P, q, A, b, K, cb.Settings())
-            return ka.assemble_kkt_matrix(data.P, data.A, cb.CompositeCone(data.cones))[0]
-        v, cbl = scale_cpu_sample(name, rate, ms, desc, note, full_kkt)
-        line = dict(metric=metric, value=v, unit="it/s", n_gpus=args.gpus, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=1e3 / v, higher_is_better=True, scaling="strong",
-                    vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                    config=dict(workload=name, sample=cbl["sample"], **{k: v_ for k, v_ in cbl.get("full_size", desc).items()
-                                                                        if k in ("N", "nnzL")}),
-                    cpu_baseline=cbl,
-                    e2e=dict(value=v, unit="it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(name, max(1, args.steps), max(0, args.warmup))), flush=True)
         return
 
+    args.warmup = max(args.warmup, 3)
     import torch
     if world > 1:
         import torch.distributed as dist
@@ -265,20 +336,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     import clarabel_jl_b200 as cb
-    from clarabel_jl_b200 import problems, lib as cblib
-    gen, kw, _, _ = WORKLOADS[name]
-    P, q, A, b, K = getattr(problems, gen)(**kw)
-    st = cb.Settings(direct_solve_method="b200")
+    problem = make_problem(name)
+    P, q, A, b, K = problem
     t0 = time.perf_counter()
-    solver = cb.Solver(P, q, A, b, K, st)
+    solver = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200"))
     t_setup = time.perf_counter() - t0
     ks = solver.kktsystem.kktsolver
-    cblib.make_settings  # noqa
-    rec = Recorder(ks, solver.cones)
-    solver.solve(max_iter=REPLAY_ITERS)
+    # ---- a complete IP solve on the GPU backend, every boundary call recorded
+    rec = Recorder(ks)
+    t0 = time.perf_counter()
+    sol = solver.solve()
+    t_ipsolve = time.perf_counter() - t0
     rec.detach()
-    replay = [s_ for s_ in rec.steps[1:] if len(s_["rhs"]) == 3] or rec.steps[-1:]
+    picked = pick_replay(rec.steps)
+    replay_ids = [i for i, _ in picked]
+    replay = [s_ for _, s_ in picked]
+    n_recorded = len(rec.steps)
+    rec.steps = None
     n, m = solver.data.n, solver.data.m
+    N = ks.KKT.shape[0]
 
     def pinned(a):
         """copy of `a` in page-locked host memory (the e2e copies are then true DMA transfers)"""
@@ -320,8 +396,9 @@ def main():
         return ms
 
     state_bytes = sum(v.nbytes for v in replay[0]["state"].values())
-    h2d = state_bytes + 3 * (n + m) * 8
-    d2h = 3 * (n + m) * 8
+    nrhs = len(replay[0]["rhs"])
+    h2d = state_bytes + nrhs * (n + m) * 8
+    d2h = nrhs * (n + m) * 8
     # ---- e2e (host buffers through the C-ABI)
     for i in range(args.warmup):
         step(i)
@@ -334,9 +411,10 @@ def main():
     ks.ldl.set_resident(True)
     for i in range(args.warmup):
         step(i)
-    ks.ldl.reset_timers()
+    ks.ldl.reset_timers(); ks.ir_rounds = 0; ks.n_solves = 0
     ms_res = timed(args.steps, args.warmup)
     tm = ks.ldl.timers()
+    ir_per_solve = ks.ir_rounds / max(1, ks.n_solves)
     stop.set(); th.join(timeout=2)
     ks.ldl.set_resident(False)
     # ---- per-kernel-class timing of the factorisation (events around each launch group; graph
@@ -345,10 +423,24 @@ def main():
     ks.ldl.set_detail(True); ks.ldl.set_resident(True)
     step(0)
     ks.ldl.reset_timers()
-    for i in range(2):
+    nd_steps = len(replay)
+    for i in range(nd_steps):
         step(i)
     td = ks.ldl.timers()
     ks.ldl.set_detail(False); ks.ldl.set_resident(False)
+    # ---- parity solves (every rank takes part; rank 0 evaluates): the LAST recorded system
+    last = replay[-1]
+    ks.ir_rounds = 0; ks.n_solves = 0
+    ok_par = ks.update(FakeCones(last["state"]))
+    nzv = ks.device_nzval()                     # unregularised K values as the device holds them
+    gsol, gfull = [], []
+    for rx, rz in last["rhs"]:
+        gx, gz = np.zeros(n), np.zeros(m)
+        ks.setrhs(rx, rz); ok_par &= ks.solve(gx, gz)
+        gsol.append(np.concatenate([gx, gz]))
+        gfull.append(ks.ldl.download(6, N))     # [x; z; expansion variables] as the device holds it
+    par_ir = ks.ir_rounds / max(1, ks.n_solves)
+    nreg = int(ks.ldl.download(5, 1)[0])
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -356,17 +448,31 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    desc = describe(name, P, A, ks)
+    import scipy.sparse as sp
+    Kd = sp.csc_matrix((nzv, ks.KKT.indices, ks.KKT.indptr), shape=ks.KKT.shape)
+    mv = sym_matvec(Kd)
+    resid = []
+    for (rx, rz), xf in zip(last["rhs"], gfull):
+        bb = np.concatenate([rx, rz, np.zeros(N - n - m)])
+        r = bb - mv(xf)
+        resid.append(float(np.abs(r).max() / max(1e-300, np.abs(bb).max())))
+    parity = dict(system=f"IP iteration {replay_ids[-1]} of {n_recorded - 1} (the last one recorded)",
+                  ok=bool(ok_par), rel_residual_unregularised_K=resid, ir_rounds_per_solve=par_ir,
+                  regularised_pivots=nreg, gpu_solve=dict(status=sol.status_name, iterations=int(sol.iterations),
+                                                          obj_val=float(sol.obj_val), obj_val_dual=float(sol.obj_val_dual),
+                                                          r_prim=float(sol.r_prim), r_dual=float(sol.r_dual)),
+                  cpu_rel_diff=None)
+    info = ks.ldl.info()
+    stats = ks.ldl.stats()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     nfac, nsol = max(1, tm["nfactor"]), max(1, tm["nsolve"])
-    N, nnzL, nnzK = desc["N"], desc["nnzL"], desc["nnzK"]
-    stats = ks.ldl.stats()
+    nnzL, nnzK = int(info.nnzL), int(ks.KKT.nnz)
     # ---- FP64 compute calibration on this box (no FP64 figure in MEASURED_PEAKS.json): cuBLAS DGEMM
     fp64_peak = None
     try:
@@ -391,55 +497,88 @@ def main():
     t_fac = tm["factor_ms"] / nfac * 1e-3
     t_spmv = tm["spmv_ms"] / nsol * 1e-3
     t_schur = td["schur_ms"] / nfd * 1e-3
+    rank_flops = stats.get("rank_flops", stats["flops"]) if world > 1 else stats["flops"]
+    traffic = load_traffic(name) or {}
     kernels = dict(
         triangular_solve_sweeps=dict(bound="hbm", ms_per_call=t_solve * 1e3, calls_per_step=nsol / args.steps,
                                      achieved=b_solve / t_solve / 1e9, unit="GB/s", peak=hbm_peak,
-                                     algorithmic_bytes=b_solve),
+                                     algorithmic_bytes=b_solve, traffic=traffic.get("triangular_solve_sweeps")),
         spmv_residual=dict(bound="hbm", ms_per_call=t_spmv * 1e3, calls_per_step=nsol / args.steps,
                            achieved=b_spmv / max(t_spmv, 1e-12) / 1e9, unit="GB/s", peak=hbm_peak,
-                           algorithmic_bytes=b_spmv),
+                           algorithmic_bytes=b_spmv, traffic=traffic.get("spmv_residual")),
         factor_total=dict(bound="fp64", ms_per_call=t_fac * 1e3, calls_per_step=nfac / args.steps,
-                          achieved=stats["flops"] / t_fac / 1e12, unit="TFLOP/s", peak=fp64_peak,
-                          algorithmic_flops=stats["flops"]),
-        k_schur_large=dict(bound="fp64", ms_per_call=t_schur * 1e3, calls_per_step=1.0,
-                           achieved=(stats["schur_flops"] / t_schur / 1e12) if t_schur > 0 else None,
-                           unit="TFLOP/s", peak=fp64_peak, algorithmic_flops=stats["schur_flops"]),
+                          achieved=rank_flops / t_fac / 1e12, unit="TFLOP/s", peak=fp64_peak,
+                          algorithmic_flops=rank_flops),
+        schur_gemm=dict(bound="fp64", ms_per_call=t_schur * 1e3, calls_per_step=1.0,
+                        achieved=(stats["schur_flops"] / t_schur / 1e12) if t_schur > 0 else None,
+                        unit="TFLOP/s", peak=fp64_peak, algorithmic_flops=stats["schur_flops"],
+                        traffic=traffic.get("schur_gemm")),
         factor_pivot_blocks=dict(ms_per_call=td["panel_ms"] / nfd), factor_small_fronts=dict(ms_per_call=td["small_ms"] / nfd),
         factor_assembly=dict(ms_per_call=td["asm_ms"] / nfd))
     for k in kernels.values():
         if k.get("peak") and k.get("achieved") is not None:
             k["frac"] = k["achieved"] / k["peak"]
-    # dominant kernel of the step: the largest (time per call x calls per step) among the measured ones
-    cand = {"triangular_solve_sweeps": t_solve * nsol / args.steps, "k_schur_large": t_schur,
+    if world > 1:
+        for k in ("schur_gemm", "factor_total"):
+            kernels[k]["note"] = "flops of the fronts THIS rank factors (own subtrees + replicated top) / this rank's time"
+    # dominant kernel class of the step: the largest (time per call x calls per step) among the measured ones
+    cand = {"triangular_solve_sweeps": t_solve * nsol / args.steps, "schur_gemm": t_schur,
             "spmv_residual": t_spmv * nsol / args.steps}
     dom = max(cand, key=cand.get)
     kd = kernels[dom]
-    roofline = dict(bound=kd["bound"], kernel=dom, achieved=kd["achieved"], peak=kd["peak"], unit=kd["unit"],
-                    frac=kd.get("frac"), traffic=None,
+    roofline = dict(bound=kd["bound"] if kd["bound"] == "hbm" else "tensor", kernel=dom, achieved=kd["achieved"],
+                    peak=kd["peak"], unit=kd["unit"], frac=kd.get("frac"), traffic=kd.get("traffic"),
                     peak_source=(peak_src if kd["bound"] == "hbm" else
                                  "on-box cuBLAS DGEMM 4096^3 (float64) - MEASURED_PEAKS.json has no FP64 figure"),
-                    note="bound 'fp64' = FP64 FMA pipe (tcgen05 has no f64 kind; see DESIGN.md section 4)",
+                    note="FP64 throughout: bound 'tensor' means the FP64 tensor-core path (DMMA; tcgen05 has no f64 "
+                         "kind, DESIGN.md section 4) measured against an on-box DGEMM",
                     kernels=kernels)
-    line = dict(metric=metric, value=args.steps / (ms_res * 1e-3), unit="it/s", n_gpus=args.gpus,
+    config = workload_config(name, solver.data, N, nnzK)
+    line = dict(metric=METRIC, value=args.steps / (ms_res * 1e-3), unit="it/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_res / args.steps,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                data="synthetic", impl="b200",
-                config=dict(desc, l2="inputs larger than L2 (no flush)", setup_s=t_setup,
-                            replayed_ip_iterations=len(replay), ordering="nd+amd"),
+                data="synthetic", impl="b200", config=config,
+                details=dict(nnzL=nnzL, factor_flops=stats["flops"], nsuper=int(stats["nsuper"]),
+                             nlevels=int(stats["nlevels"]),
+                             ordering=ORDERING_NAMES.get(int(stats.get("ordering_used", -1)), "?"),
+                             setup_s=t_setup, ip_solve_s=t_ipsolve, recorded_ip_iterations=n_recorded - 1,
+                             replayed_ip_iterations=replay_ids,
+                             solves_per_step=nsol / args.steps, ir_rounds_per_solve=ir_per_solve),
                 e2e=dict(value=args.steps / (ms_e2e * 1e-3), unit="it/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                gpu_launches=int(tm["nlaunch"]), clocks=clocks_summary(samples), roofline=roofline)
-    if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N = 1 only
-        try:
-            rate, ms, sdesc, note = cpu_sample(name, 1, 1)
-            line["cpu_baseline"] = scale_cpu_sample(name, rate, ms, sdesc, note, lambda: ks.KKT)[1]
-        except Exception as e:                      # the GPU measurement above must still be reported
-            line["cpu_baseline"] = dict(value=None, unit="it/s", cores=1, kind="port",
-                                        sample=f"CPU leg failed: {type(e).__name__}: {e}")
-    print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+                gpu_launches=int(tm["nlaunch"]), clocks=clocks_summary(samples), roofline=roofline,
+                parity=parity,
+                cpu_baseline=dict(value=None, unit="it/s", cores=1, kind="port",
+                                  sample="pending: the full-size CPU step runs after this line"))
+    if world > 1 or args.no_cpu_baseline:
+        line["cpu_baseline"]["sample"] = "not run (the CPU arm is timed at N = 1 only)" if world > 1 else "not run (--no-cpu-baseline)"
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    # the GPU measurement is on record before the (long) CPU leg starts
+    print(json.dumps(line), flush=True)
+    out = {}
+    thc = threading.Thread(target=cpu_full_step, args=(problem, last, out), daemon=True)
+    t0 = time.perf_counter()
+    thc.start(); thc.join(CPU_LEG_LIMIT_S)
+    what = (f"FULL-SIZE instance, one step (update + 3 solves with refinement) on the system of IP iteration "
+            f"{replay_ids[-1]}; oracle/qdldl_oracle.c, 1 thread, AMD-class ordering with amd_dense_scale = 1.5")
+    if thc.is_alive() or "seconds" not in out:
+        why = out.get("error") or f"not finished within the {CPU_LEG_LIMIT_S:.0f} s wall-clock limit of the CPU leg"
+        line["cpu_baseline"] = dict(value=None, unit="it/s", cores=1, kind="port", sample=what + " -- " + why)
+    else:
+        line["cpu_baseline"] = dict(value=1.0 / out["seconds"], unit="it/s", cores=1, kind="port", sample=what,
+                                    step_seconds=out["seconds"], factor_seconds=out["factor_seconds"],
+                                    setup_seconds=out["setup_seconds"], nnzL=out["nnzL"],
+                                    factor_flops=out["factor_flops"])
+        diffs = [float(np.abs(g - c).max() / max(1e-300, np.abs(c).max())) for g, c in zip(gsol, out["sols"])]
+        line["parity"]["cpu_rel_diff"] = diffs
+        line["parity"]["cpu_ok"] = out["ok"]
+    print(json.dumps(line), flush=True)
+    if thc.is_alive():
+        os._exit(0)          # the C factorisation cannot be interrupted; everything is already printed
 
 
 if __name__ == "__main__":

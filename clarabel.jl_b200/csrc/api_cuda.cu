@@ -218,6 +218,10 @@ struct cb200_handle {
     DevBuf<int8_t> d_active, d_keepcol, d_topcolkeep;
     DevBuf<int32_t> d_top_list;
     GraphExec g_factor[2], g_solve;     // CUDA graphs: factor (without/with static reg), solve sweeps
+    // grow-only device staging for the inner-boundary uploads (update_values!/scale_values!/update_P/A):
+    // no cudaMalloc / cudaFree per call and no stream sync for pageable caller buffers
+    DevBuf<int64_t> d_stage_idx; DevBuf<double> d_stage_val;
+    size_t stage_idx_cap = 0, stage_val_cap = 0;
     Timers tm;
 };
 
@@ -831,26 +835,57 @@ void cb200_destroy(cb200_handle* h) {
     if (s) cudaStreamDestroy(s);
 }
 
+// Staging for the inner-boundary uploads.  The reference issues ~5 update_values!/scale_values! calls
+// per sparse cone per iteration (directldl_datamaps.jl:61-79), so these calls must not allocate or
+// synchronise: the device staging buffers only grow, and the stream is ordered, so the kernel of
+// call k+1 cannot overtake the copy of call k.  The staging buffer is reused by the next call only
+// after the previous kernel was enqueued behind its copy on the same stream; the H2D copies from
+// pageable host memory return after the source has been staged by the driver, so the caller may
+// overwrite `index` / `values` on return.
+// Page-locked caller buffers make cudaMemcpyAsync truly asynchronous: then (and only then) the call
+// must wait for the copy before returning, because the caller may overwrite its buffer.
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int stage_reserve(cb200_handle* h, size_t nidx, size_t nval) {
+    if (nidx > h->stage_idx_cap) {
+        CUDA_OK(cudaStreamSynchronize(h->stream));          // the old buffer may still be in use
+        size_t cap = std::max(nidx, std::max<size_t>(4096, 2 * h->stage_idx_cap));
+        CUDA_OK(h->d_stage_idx.alloc(cap)); h->stage_idx_cap = cap;
+    }
+    if (nval > h->stage_val_cap) {
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        size_t cap = std::max(nval, std::max<size_t>(4096, 2 * h->stage_val_cap));
+        CUDA_OK(h->d_stage_val.alloc(cap)); h->stage_val_cap = cap;
+    }
+    return 0;
+}
+
 int32_t cb200_update_values(cb200_handle* h, const int64_t* index, const double* values, int64_t len) {
     if (len <= 0) return 0;
-    DevBuf<int64_t> di; DevBuf<double> dv;
-    CUDA_OK(di.alloc(len)); CUDA_OK(dv.alloc(len));
-    CUDA_OK(cudaMemcpyAsync(di.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(cudaMemcpyAsync(dv.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, di.p, dv.p, len, h->base);
+    CUDA_OK(cudaSetDevice(h->st.device));
+    { int rc = stage_reserve(h, (size_t)len, (size_t)len); if (rc) return rc; }
+    CUDA_OK(cudaMemcpyAsync(h->d_stage_idx.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_stage_val.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, h->d_stage_idx.p, h->d_stage_val.p, len, h->base);
     LAUNCH(h);
-    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    if (host_is_pinned(index) || host_is_pinned(values)) CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 int32_t cb200_scale_values(cb200_handle* h, const int64_t* index, int64_t len, double scale) {
     if (len <= 0) return 0;
-    DevBuf<int64_t> di;
-    CUDA_OK(di.alloc(len));
-    CUDA_OK(cudaMemcpyAsync(di.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    k_scale_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, di.p, scale, len, h->base);
+    CUDA_OK(cudaSetDevice(h->st.device));
+    { int rc = stage_reserve(h, (size_t)len, 0); if (rc) return rc; }
+    CUDA_OK(cudaMemcpyAsync(h->d_stage_idx.p, index, len * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    k_scale_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, h->d_stage_idx.p, scale, len, h->base);
     LAUNCH(h);
-    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    if (host_is_pinned(index)) CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -871,6 +906,7 @@ static int finish_factor(cb200_handle* h) {
 }
 
 int32_t cb200_refactor(cb200_handle* h) {
+    CUDA_OK(cudaSetDevice(h->st.device));
     int rc = factor(h, /*static_reg=*/false);
     if (rc) return rc;
     return finish_factor(h);
@@ -879,6 +915,7 @@ int32_t cb200_refactor(cb200_handle* h) {
 int32_t cb200_solve(cb200_handle* h, double* x, const double* b) {
     const int64_t N = h->N;
     if (N == 0) return 0;
+    CUDA_OK(cudaSetDevice(h->st.device));
     CUDA_OK(cudaMemcpyAsync(h->d_b.p, b, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     int rc = tri_solve(h, h->d_b.p, h->d_x.p);
     if (rc) return rc;
@@ -902,6 +939,7 @@ int32_t cb200_set_maps(cb200_handle* h, int64_t n, int64_t m, int64_t p,
                        const int64_t* map_soc_u, const int64_t* map_soc_v, const int64_t* map_soc_D) {
     try {
         if (n + m + p != h->N) { set_error("cb200_set_maps: n+m+p != N"); return -2; }
+        CUDA_OK(cudaSetDevice(h->st.device));
         const int64_t base = h->base;
         cudaStream_t s = h->stream;
         h->n = n; h->m = m; h->p = p;
@@ -1000,6 +1038,7 @@ int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_e
                            const double* soc_d, const double* soc_u, const double* soc_v,
                            const double* psd_R) {
     if (!h->maps_set) { set_error("cb200_update_cones: cb200_set_maps not called"); return -2; }
+    CUDA_OK(cudaSetDevice(h->st.device));
     cudaStream_t st = h->stream;
     h->tm.begin(Timers::CONE, st);
     auto h2d = [&](double* dst, const double* src, int64_t len) -> cudaError_t {
@@ -1046,9 +1085,10 @@ int32_t cb200_update_cones(cb200_handle* h, const double* w, const double* soc_e
 int32_t cb200_setrhs(cb200_handle* h, const double* rhsx, const double* rhsz) {
     if (!h->maps_set) { set_error("cb200_setrhs: cb200_set_maps not called"); return -2; }
     if (h->resident) return 0;
+    CUDA_OK(cudaSetDevice(h->st.device));
     cudaStream_t st = h->stream;
-    if (h->n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, h->n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (h->m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, h->m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h->n && rhsx) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, h->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h->m && rhsz) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, h->m * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));        // the caller may overwrite its buffers on return
     return 0;
 }
@@ -1056,13 +1096,14 @@ int32_t cb200_setrhs(cb200_handle* h, const double* rhsx, const double* rhsz) {
 int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
                        double* lhsx, double* lhsz, int32_t* ir_rounds) {
     if (!h->maps_set) { set_error("cb200_solve_ir: cb200_set_maps not called"); return -2; }
+    CUDA_OK(cudaSetDevice(h->st.device));
     cudaStream_t st = h->stream;
     const int64_t N = h->N, n = h->n, m = h->m;
     if (ir_rounds) *ir_rounds = 0;
     if (N == 0) return 0;
-    if (!h->resident && (rhsx || rhsz)) {
-        if (n) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
-        if (m) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!h->resident) {      // each part is optional on its own (a NULL part keeps what cb200_setrhs stored)
+        if (n && rhsx) CUDA_OK(cudaMemcpyAsync(h->d_rx.p, rhsx, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (m && rhsz) CUDA_OK(cudaMemcpyAsync(h->d_rz.p, rhsz, m * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     k_build_rhs<<<nblk(N, 256), 256, 0, st>>>(h->d_rx.p, h->d_rz.p, n, m, N, h->d_b.p);
     CUDA_OK(cudaMemsetAsync(h->d_scal.p + 1, 0, sizeof(unsigned long long), st));
@@ -1112,6 +1153,13 @@ int32_t cb200_solve_ir(cb200_handle* h, const double* rhsx, const double* rhsz,
     }
     CUDA_OK(cudaStreamSynchronize(st));
     h->tm.collect();
+    if (!ok && !h->resident) {
+        // a failed solve must not leave stale finite values in the caller's vectors: the reference
+        // checks all(isfinite, x) on them when refinement is disabled (kktsolver_directldl.jl:356-370)
+        const double qnan = std::numeric_limits<double>::quiet_NaN();
+        if (lhsx) std::fill(lhsx, lhsx + n, qnan);
+        if (lhsz) std::fill(lhsz, lhsz + m, qnan);
+    }
     return ok ? 0 : 1;
 }
 
@@ -1119,18 +1167,20 @@ static int32_t update_block(cb200_handle* h, const DevBuf<int64_t>& map, const d
     if (!h->maps_set) { set_error("cb200_update_P/A: cb200_set_maps not called"); return -2; }
     if ((int64_t)map.n != len) { set_error("cb200_update_P/A: length mismatch"); return -2; }
     if (len == 0) return 0;
-    DevBuf<double> dv;
-    CUDA_OK(dv.alloc(len));
-    CUDA_OK(cudaMemcpyAsync(dv.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, map.p, dv.p, len, 0);
+    CUDA_OK(cudaSetDevice(h->st.device));
+    { int rc = stage_reserve(h, 0, (size_t)len); if (rc) return rc; }
+    CUDA_OK(cudaMemcpyAsync(h->d_stage_val.p, values, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_update_values<<<nblk(len, 256), 256, 0, h->stream>>>(h->d_nz.p, map.p, h->d_stage_val.p, len, 0);
     LAUNCH(h);
-    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    if (host_is_pinned(values)) CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 int32_t cb200_update_P(cb200_handle* h, const double* values, int64_t len) { return update_block(h, h->d_mapP, values, len); }
 int32_t cb200_update_A(cb200_handle* h, const double* values, int64_t len) { return update_block(h, h->d_mapA, values, len); }
 
 int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len) {
+    CUDA_OK(cudaSetDevice(h->st.device));
     cudaStream_t st = h->stream;
     const double* src = nullptr; int64_t n = 0;
     switch (what) {
@@ -1144,6 +1194,7 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len) 
                   unsigned int v = 0;
                   CUDA_OK(cudaMemcpyAsync(&v, h->d_nreg.p, sizeof(v), cudaMemcpyDeviceToHost, st));
                   CUDA_OK(cudaStreamSynchronize(st)); out[0] = (double)v; return 0; }
+        case 6: src = h->d_x.p; n = h->N; break;       // full solution [x; z; expansion variables] of the last solve
         default: set_error("download: bad selector"); return -2;
     }
     if (len != n) { set_error("download: length mismatch"); return -2; }
@@ -1230,8 +1281,12 @@ const char* cb200_fine_timer_name(int32_t i) { return (i >= 0 && i < Timers::NFI
 int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
     const Symbolic& S = h->S;
     double schur = 0, panel_large = 0, big_bytes = 0, nlarge = 0;
+    double my_flops = 0;
     for (int32_t sn = 0; sn < S.nsuper; ++sn) {
         const double ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
+        // multi-GPU: only the fronts THIS rank factors (its own subtrees + the replicated top)
+        if (h->dist && !h->is_top[sn] && h->owner[sn] != h->rank) continue;
+        for (double k = 0; k < ns; ++k) my_flops += (nf - k) * (nf - k);
         if (h->to_large((int)nf, (int)ns)) {
             nlarge += 1;
             schur += nr * (nr + 1.0) * ns;                 // flops of F22 -= L21 D L21' (lower part)
@@ -1239,9 +1294,10 @@ int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
         }
         if (nf * ns >= 65536 && ns > 32) big_bytes += 8.0 * nf * ns;
     }
-    double v[10] = {S.flops, schur, panel_large - schur, (double)S.nnzL, (double)S.nlevels, (double)S.nsuper,
-                    nlarge, big_bytes, (double)S.upd_total * 8.0, (double)S.panel_off.back() * 8.0};
-    for (int i = 0; i < len && i < 10; ++i) out[i] = v[i];
+    double v[12] = {S.flops, schur, panel_large - schur, (double)S.nnzL, (double)S.nlevels, (double)S.nsuper,
+                    nlarge, big_bytes, (double)S.upd_total * 8.0, (double)S.panel_off.back() * 8.0,
+                    (double)S.ordering_used, my_flops};
+    for (int i = 0; i < len && i < 12; ++i) out[i] = v[i];
     return 0;
 }
 

@@ -97,6 +97,7 @@ int64_t cb200_symbolic_stat(const cb200_symbolic* s, int32_t what) {
         case 4: return S.max_front; case 5: return S.max_width; case 6: return S.upd_total;
         case 7: return S.panel_off.empty() ? 0 : S.panel_off.back();
         case 8: return (int64_t)S.rows.size(); case 9: return S.nnzK;
+        case 10: return S.ordering_used;
     }
     return -1;
 }

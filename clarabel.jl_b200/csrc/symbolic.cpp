@@ -109,9 +109,12 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
     std::vector<int32_t> p0(N);
     if (user_perm) {
         for (int32_t i = 0; i < N; ++i) p0[i] = (int32_t)user_perm[i];
+        S.ordering_used = 3;
     } else if (opt.ordering == 2) {
         std::iota(p0.begin(), p0.end(), 0);
+        S.ordering_used = 2;
     } else {
+        S.ordering_used = 0;
         std::vector<int64_t> xadj; std::vector<int32_t> adj;
         build_sym_graph(N, colptr, rowval, xadj, adj);
         if (opt.ordering != 1) {
@@ -147,7 +150,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             if (split) {
                 for (int32_t k = 0; k < N; ++k) ipn[pn[k]] = k;
                 ordering_cost(N, colptr, rowval, ipn, opt.nd_max_cost_ratio * fa, &ab);
-                if (!ab) p0.swap(pn);
+                if (!ab) { p0.swap(pn); S.ordering_used = 1; }
                 lap("  nd cost + arbitration");
             }
         }

@@ -58,6 +58,7 @@ struct Symbolic {
     double flops = 0;               // sum over pivot columns of (col length incl. diag)^2
     int64_t upd_total = 0;          // doubles in update storage
     int32_t max_front = 0, max_width = 0;
+    int32_t ordering_used = 0;      // 0 = AMD-class, 1 = nested dissection, 2 = natural, 3 = caller's permutation
     inline int32_t ns(int32_t s) const { return sn_first[s + 1] - sn_first[s]; }
     inline int32_t nr(int32_t s) const { return (int32_t)(rows_ptr[s + 1] - rows_ptr[s]); }
 };

@@ -113,10 +113,10 @@ class B200DirectLDLSolver:
         return {self._L.cb200_fine_timer_name(i).decode(): float(out[i]) for i in range(n)}
 
     def stats(self):
-        out = np.zeros(10)
-        self._L.cb200_get_stats(self._h, _p(out), 10)
+        out = np.zeros(12)
+        self._L.cb200_get_stats(self._h, _p(out), 12)
         keys = ["flops", "schur_flops", "panel_flops", "nnzL", "nlevels", "nsuper", "nlarge",
-                "big_solve_bytes", "upd_bytes", "panel_bytes"]
+                "big_solve_bytes", "upd_bytes", "panel_bytes", "ordering_used", "rank_flops"]
         return dict(zip(keys, out.tolist()))
 
     def reset_timers(self):

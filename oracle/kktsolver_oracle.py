@@ -148,6 +148,8 @@ class OracleDirectLDLKKTSolver:
     """DirectLDLKKTSolver{Float64} with the :qdldl engine, on the host."""
 
     literal_soc_updates = False     # True: issue the reference's 5 calls per sparse SOC
+    amd_dense_scale = 1.5           # the reference's value (directldl_qdldl.jl:18-25); the full-size parity
+                                    # tests lower it to shorten the host ordering (any permutation is valid)
 
     def __init__(self, P, A, cones, m, n, settings, perm=None):
         pkg = _pkg()
@@ -162,6 +164,8 @@ class OracleDirectLDLKKTSolver:
         self.Hsblocks = np.zeros(int(cones.rng_blocks[-1]))
         self.diagonal_regularizer = 0.0
         st = settings
+        if perm is None and self.amd_dense_scale != 1.5:
+            perm = _q.amd_order(self.KKT, self.amd_dense_scale)
         self.ldl = _q.QDLDLFactorisation(
             self.KKT, self.Dsigns, eps=st.dynamic_regularization_eps,
             delta=st.dynamic_regularization_delta, perm=perm,

@@ -1,0 +1,135 @@
+"""GPU parity at the BASELINE.json sizes (run with -m gpu on the B200 box).
+
+north_star: "results must match the reference QDLDL path on the same problems (primal/dual
+objective and residuals within 1e-6 relative; identical status codes)".  The template is the
+reference's linear-solver matrix test (test/OptTests/linear_solvers.jl:11-71): the same problem
+through two `direct_solve_method`s.
+
+  C2, C3  whole solves on both arms: identical status and iteration count, objectives and residual
+          measures within 1e-6 (C2 is also the one workload whose root front has > 2048 children,
+          i.e. the only user of k_assemble_atomic).
+  C5, C4  a whole CPU solve would take hours (one QDLDL factorisation of C5 is ~2.5 min), so the GPU
+          solve runs to completion and its LATE systems (mu <= 1e-6: the badly scaled ones) are
+          checked: relative residual against the unregularised K by a host SpMV (independent of the
+          factorisation), no runaway dynamic regularisation, and - C5 - the last system re-solved
+          by the CPU oracle, solutions within 1e-6.
+
+The oracle uses amd_dense_scale = 0.3 here (instead of the reference's 1.5) only to shorten the host
+ordering of the factor-model graph; any permutation is a valid input to LDL'.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _rel(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+@pytest.fixture(scope="module")
+def fast_oracle(cb):
+    from oracle.kktsolver_oracle import OracleDirectLDLKKTSolver
+    old = OracleDirectLDLKKTSolver.amd_dense_scale
+    OracleDirectLDLKKTSolver.amd_dense_scale = 0.3
+    yield OracleDirectLDLKKTSolver
+    OracleDirectLDLKKTSolver.amd_dense_scale = old
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_whole_solve_parity_at_size(cb, fast_oracle, name):
+    import bench
+    P, q, A, b, K = bench.make_problem(name)
+    sg = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200")).solve()
+    so = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="qdldl")).solve()
+    assert sg.status_name == so.status_name == "SOLVED"
+    assert sg.iterations == so.iterations
+    assert _rel(sg.obj_val, so.obj_val) < 1e-6 and _rel(sg.obj_val_dual, so.obj_val_dual) < 1e-6
+    assert abs(sg.r_prim - so.r_prim) < 1e-6 and abs(sg.r_dual - so.r_dual) < 1e-6
+    assert np.abs(sg.x - so.x).max() < 1e-5 * max(1.0, np.abs(so.x).max())
+
+
+def _gpu_solve_recorded(cb, name):
+    import bench
+    problem = bench.make_problem(name)
+    P, q, A, b, K = problem
+    solver = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200"))
+    ks = solver.kktsystem.kktsolver
+    rec = bench.Recorder(ks)
+    sol = solver.solve()
+    rec.detach()
+    mus = [row[5] for row in solver.iter_log]          # mu at the start of every iteration
+    return problem, solver, ks, rec.steps, sol, mus
+
+
+def _late_system_residuals(ks, steps, nlate):
+    """Replays the last `nlate` recorded systems on the device; returns the relative residuals
+    ||b - K x||_inf / ||b||_inf against the unregularised K (host SpMV), the full device
+    solutions of the LAST one and the regularised-pivot counts."""
+    import bench
+    n, m = ks.n, ks.m
+    N = ks.KKT.shape[0]
+    full = [s for s in steps if len(s["rhs"]) == 3]
+    out, last_sols, nregs = [], None, []
+    for st in full[-nlate:]:
+        assert ks.update(bench.FakeCones(st["state"]))
+        nregs.append(int(ks.ldl.download(5, 1)[0]))
+        Kd = sp.csc_matrix((ks.device_nzval(), ks.KKT.indices, ks.KKT.indptr), shape=ks.KKT.shape)
+        mv = bench.sym_matvec(Kd)
+        sols = []
+        for rx, rz in st["rhs"]:
+            gx, gz = np.zeros(n), np.zeros(m)
+            ks.setrhs(rx, rz); assert ks.solve(gx, gz)
+            xf = ks.ldl.download(6, N)
+            bb = np.concatenate([rx, rz, np.zeros(N - n - m)])
+            out.append(float(np.abs(bb - mv(xf)).max() / np.abs(bb).max()))
+            sols.append(np.concatenate([gx, gz]))
+        last_sols = sols
+    return out, last_sols, nregs, full[-1]
+
+
+def test_c5_late_systems_vs_oracle(cb):
+    import bench
+    problem, solver, ks, steps, sol, mus = _gpu_solve_recorded(cb, "C5")
+    assert sol.status_name == "SOLVED"
+    assert min(mus) <= 1e-6                      # the replayed systems really are late iterates
+    resid, gsol, nregs, last = _late_system_residuals(ks, steps, 3)
+    # the reference's own refinement target is 1e-12 + 1e-13 ||b|| (settings.jl:127-132)
+    assert max(resid) < 1e-9, resid
+    assert max(nregs) == 0, nregs
+    # the last system once more on the CPU QDLDL path (reference ordering parameters)
+    out = {}
+    bench.cpu_full_step(problem, last, out)
+    assert "error" not in out, out.get("error")
+    assert out["ok"]
+    for g, c in zip(gsol, out["sols"]):
+        assert np.abs(g - c).max() <= 1e-6 * max(1e-300, np.abs(c).max())
+
+
+def test_c4_full_size_sdp(cb):
+    """200 x PSDTriangleConeT(50): 1275-wide dense cone blocks, 1.63e8 Hs entries written by the
+    skron kernel (coneops_psdtrianglecone.jl:502-540).  Whole GPU solve, late systems checked."""
+    problem, solver, ks, steps, sol, mus = _gpu_solve_recorded(cb, "C4")
+    assert sol.status_name == "SOLVED"
+    assert sol.r_prim < 1e-7 and sol.r_dual < 1e-7
+    assert _rel(sol.obj_val, sol.obj_val_dual) < 1e-6
+    resid, _, nregs, last = _late_system_residuals(ks, steps, 2)
+    assert max(resid) < 1e-8, resid
+    # skron at side 50 against the oracle's literal restatement, one cone of the last state
+    from oracle.kktsolver_oracle import skron_triu
+    R = last["state"]["psd_R"][:2500].reshape(50, 50, order="F")
+    Hs = skron_triu(R @ R.T)
+    ti, tj = np.tril_indices(Hs.shape[0])
+    want = -Hs[tj, ti]
+    cones = solver.cones
+    i0 = [i for i, t in enumerate(cones.types) if t == cb.cones.PSD][0]
+    assert ks.update(__import__("bench").FakeCones(last["state"]))
+    got = ks.device_nzval()[ks.map.Hsblocks[cones.rng_blocks[i0]:cones.rng_blocks[i0 + 1]]]
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
