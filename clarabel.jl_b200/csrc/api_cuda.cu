@@ -44,20 +44,14 @@ template <class T> struct DevBuf {
     ~DevBuf() { free(); }
 };
 
-struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpanel = 0; bool many_children = false; };
+struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpanel = 0; bool many_children = false;
+               int32_t schur_t128 = 0, schur_t64 = 0; };      // max over the fronts of the number of update-block tiles per side
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
 constexpr int NPANEL = 4;
 static const int kPanelDoubles[NPANEL] = {4096, 9000, 16000, 1 << 30};   // smem need classes (doubles)
 constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
-
-// fronts handled by k_factor_panel: 64 < nf <= 152 (panel + scratch in one CTA's shared memory)
-inline bool panel_eligible(int nf, int ns, int min_nf = 64, int max_nf = 152) {
-    // (measured: extending this to narrow fronts up to nf = 320 moves work from the pivot-block
-    // kernels to 1-CTA-per-SM panels and is a net loss on C5, so the range stays 64 < nf <= 152)
-    return nf > min_nf && nf <= max_nf && ns <= 150 && ((int64_t)nf * ns + (int64_t)nf * 25) <= 27000;
-}
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -74,7 +68,7 @@ struct Timers {
     enum { F_SMALL0 = 0, F_PANEL0 = 6, F_ZERO = 10, F_ASM = 11, F_DIAG = 12, F_ROWS = 13, F_SCHUR = 14, F_FINISH = 15,
            F_PROLOGUE = 16, F_FWD_LEAF = 17, F_FWD_SUB = 18, F_FWD_WARP = 19, F_FWD_CTA = 20, F_FWD_BIG_ASM = 21,
            F_FWD_BIG_TRI = 22, F_FWD_BIG_GEMV = 23, F_BWD_LEAF = 24, F_BWD_SUB = 25, F_BWD_WARP = 26, F_BWD_CTA = 27,
-           F_BWD_BIG_GEMV = 28, F_BWD_BIG_TRI = 29, F_PERMUTE = 30, F_COMM = 31, NFINE = 32 };
+           F_BWD_BIG_GEMV = 28, F_BWD_BIG_TRI = 29, F_PERMUTE = 30, F_COMM = 31, F_PANELUPD = 32, NFINE = 33 };
     static constexpr int NPH = NCOARSE + NFINE;
     double ms[NPH] = {};
     double nfactor = 0, nsolve = 0, nlaunch = 0;
@@ -165,7 +159,7 @@ struct cb200_handle {
     DevBuf<int8_t> d_dsign_perm, d_dsign_orig;
     DevBuf<int32_t> d_perm;
     // symbolic
-    DevBuf<int32_t> d_sn_first, d_rows, d_rel, d_child_ptr, d_child_list, d_batches;
+    DevBuf<int32_t> d_sn_first, d_rows, d_rel, d_child_ptr, d_child_list, d_batches, d_ld;
     DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff, d_front_ptr, d_asm_base;
     DevBuf<int32_t> d_asm_colptr, d_asm_src, d_asm_child;
     // numeric
@@ -201,14 +195,17 @@ struct cb200_handle {
     double last_eps = 0;
     bool resident = false;
     int detail = 0;            // 1: per-phase event timing, 2: also per kernel class (both disable graph replay)
-    bool use_panel_kernel = true;
     // size-class boundaries of the factorisation plan (tuning knobs, environment variables
-    // CB200_PANEL_MIN_NF / CB200_PANEL_MAX_NF / CB200_SMALL_MAX_NF; defaults = measured best on C3/C5):
-    // panel kernel for panel_min_nf < nf <= panel_max_nf, shared-memory front kernel up to
-    // small_max_nf, pivot-block (large) path above
-    int panel_min_nf = 64, panel_max_nf = 152, small_max_nf = 152;
-    bool to_panel(int nf, int ns) const { return use_panel_kernel && panel_eligible(nf, ns, panel_min_nf, panel_max_nf); }
-    bool to_large(int nf, int ns) const { return nf > small_max_nf && !to_panel(nf, ns); }
+    // CB200_PANEL_MIN_NF / CB200_PANEL_MAX_NF / CB200_SMALL_MAX_NF / CB200_NO_PANEL, read once into the
+    // symbolic options because the large path pads its panels): panel kernel for
+    // panel_min_nf < nf <= panel_max_nf, shared-memory front kernel up to small_max_nf, pivot-block
+    // (large) path above
+    SymbolicOptions opt;
+    bool to_panel(int nf, int ns) const { return front_to_panel(opt, nf, ns); }
+    bool to_large(int nf, int ns) const { return front_is_large(opt, nf, ns); }
+    // TMA descriptors of the large-front panels (one CUtensorMap per large front)
+    bool use_tma = false; int tma_kmajor = 1;
+    DevBuf<CUtensorMap> d_tmaps; DevBuf<int32_t> d_tmap_of;
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -231,7 +228,7 @@ DevSym devsym(cb200_handle* h) {
     DevSym d;
     d.sn_first = h->d_sn_first.p; d.rows_ptr = h->d_rows_ptr.p; d.rows = h->d_rows.p; d.rel = h->d_rel.p;
     d.child_ptr = h->d_child_ptr.p; d.child_list = h->d_child_list.p;
-    d.panel_off = h->d_panel_off.p; d.upd_off = h->d_upd_off.p; d.dsign = h->d_dsign_perm.p;
+    d.panel_off = h->d_panel_off.p; d.upd_off = h->d_upd_off.p; d.dsign = h->d_dsign_perm.p; d.ld = h->d_ld.p;
     d.front_ptr = h->d_front_ptr.p; d.asm_base = h->d_asm_base.p; d.asm_colptr = h->d_asm_colptr.p;
     d.asm_src = h->d_asm_src.p; d.asm_child = h->d_asm_child.p;
     d.active = h->dist ? h->d_active.p : nullptr;
@@ -393,6 +390,59 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
 }
 
 
+// One CUtensorMap per large front: the nf x ns panel (leading dimension ld, a multiple of 8) viewed
+// as a 3-D tensor so that one TMA box is a 128-row x 16-k operand tile in a DMMA-friendly layout
+// (see k_ldl_update_tma).  The encoder lives in libcuda; it is fetched through the runtime
+// (cudaGetDriverEntryPoint) so that the library has no link-time dependency on the driver.
+// CB200_NO_TMA=1 selects the LDG fallback kernel.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int build_tensor_maps(cb200_handle* h) {
+    const Symbolic& S = h->S;
+    h->use_tma = false;
+    if (const char* e = getenv("CB200_NO_TMA")) if (e[0] == '1') return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return 0; }
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
+    std::vector<int32_t> map_of(S.nsuper, -1);
+    std::vector<CUtensorMap> maps;
+    int kmajor = 1;
+    if (const char* e = getenv("CB200_TMA_NATURAL")) if (e[0] == '1') kmajor = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        maps.clear(); std::fill(map_of.begin(), map_of.end(), -1);
+        bool ok = true;
+        for (int32_t sn = 0; sn < S.nsuper && ok; ++sn) {
+            const int ns = S.ns(sn), nf = ns + S.nr(sn);
+            if (!h->to_large(nf, ns)) continue;
+            const cuuint64_t ld = (cuuint64_t)S.panel_ld[sn];
+            CUtensorMap m;
+            cuuint64_t dims[3], strides[2]; cuuint32_t box[3], estr[3] = {1, 1, 1};
+            if (kmajor) { dims[0] = 8; dims[1] = (cuuint64_t)ns; dims[2] = ld / 8; strides[0] = ld * 8; strides[1] = 64;
+                          box[0] = 8; box[1] = TK; box[2] = TB / 8; }
+            else        { dims[0] = 8; dims[1] = ld / 8; dims[2] = (cuuint64_t)ns; strides[0] = 64; strides[1] = ld * 8;
+                          box[0] = 8; box[1] = TB / 8; box[2] = TK; }
+            CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)(h->d_L.p + S.panel_off[sn]), dims, strides,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { ok = false; break; }
+            map_of[sn] = (int32_t)maps.size(); maps.push_back(m);
+        }
+        if (ok) { h->use_tma = true; h->tma_kmajor = kmajor; break; }
+        if (kmajor == 0) break;
+        kmajor = 0;                              // retry with the natural dimension order
+    }
+    if (!h->use_tma) return 0;
+    if (maps.empty()) maps.resize(1);
+    CUDA_OK(h->d_tmaps.alloc(maps.size()));
+    CUDA_OK(cudaMemcpyAsync(h->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h->d_tmap_of.upload(map_of, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // Builds the per-level launch plans.  In multi-GPU mode a rank only schedules the supernodes it
 // owns plus the replicated top fronts (which always take the large-front / big-solve paths so
 // that assembly, all-reduce and factorisation are separate steps).
@@ -412,6 +462,10 @@ int build_plans(cb200_handle* h) {
             b.maxnr = std::max(b.maxnr, S.nr(sn));
             b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn) + 25 * nf);      // smem need of k_factor_panel
             if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
+            if (large && S.nr(sn) > 0) {
+                b.schur_t128 = std::max(b.schur_t128, (nf - 1) / TB - S.ns(sn) / TB + 1);
+                b.schur_t64 = std::max(b.schur_t64, (nf - 1) / GBM - S.ns(sn) / GBM + 1);
+            }
             batches.push_back(sn);
             woff.push_back(large ? w : 0);
             if (large) w += (int64_t)nblk(S.ns(sn), PB) * PB * PB;   // parked diagonal blocks
@@ -428,7 +482,7 @@ int build_plans(cb200_handle* h) {
             }
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
-            if (nf > h->small_max_nf) c = NSMALL;
+            if (h->to_large(nf, S.ns(sn)) || nf > kSmallNf[NSMALL - 1]) c = NSMALL;
             if (h->to_panel(nf, S.ns(sn))) {
                 int pc = 0; while (nf * S.ns(sn) + 25 * nf > kPanelDoubles[pc]) ++pc;
                 pcl[pc].push_back(sn);
@@ -465,9 +519,9 @@ int allreduce_fronts(cb200_handle* h, const Batch& B, const std::vector<int32_t>
     NCCL_OK(g_nccl.GroupStart());
     for (int32_t k = 0; k < B.cnt; ++k) {
         const int32_t sn = list[k];
-        const int64_t ns = S.ns(sn), nr = S.nr(sn), nf = ns + nr;
+        const int64_t ns = S.ns(sn), nr = S.nr(sn), ld = S.panel_ld[sn];
         double* Lp = h->d_L.p + S.panel_off[sn];
-        NCCL_OK(g_nccl.AllReduce(Lp, Lp, (size_t)(nf * ns), ncclDouble, ncclSum, h->comm, h->stream));
+        NCCL_OK(g_nccl.AllReduce(Lp, Lp, (size_t)(ld * ns), ncclDouble, ncclSum, h->comm, h->stream));
         if (nr > 0) {
             double* Us = h->d_U.p + S.upd_off[sn];
             NCCL_OK(g_nccl.AllReduce(Us, Us, (size_t)(nr * nr), ncclDouble, ncclSum, h->comm, h->stream));
@@ -587,29 +641,43 @@ int factor_body(cb200_handle* h, bool static_reg) {
                 if (rc) return rc;
             }
             if (h->detail) { h->tm.end(st); h->tm.begin(Timers::PANEL, st); }
-            const size_t sm64 = (size_t)(GSM + 2 * PB * (PB + 1)) * sizeof(double);
+            const size_t smrows = (size_t)(2 * PB * (PB + 1)) * sizeof(double);
+            // one update launch (either version): mode 0 = panel step at pivot block J0, mode 1 = Schur
+            auto launch_update = [&](int mode, int J0) {
+                const int T = h->use_tma ? TB : GBM;
+                int gx, na = 1;
+                if (mode == 0) {
+                    const int tj0 = (J0 + PB) / T;
+                    const int nbt = (B.maxns - 1) / T - tj0 + 1;          // panel column tiles still to update
+                    na = (B.maxnf - 1) / T - tj0 + 1;
+                    if (nbt <= 0 || na <= 0) return;
+                    gx = nbt * na;
+                } else {
+                    const int t = h->use_tma ? B.schur_t128 : B.schur_t64;
+                    if (t <= 0) return;
+                    gx = t * (t + 1) / 2;
+                }
+                if (h->use_tma)
+                    k_ldl_update_tma<<<dim3(gx, B.cnt), TMA_THREADS, TMA_GEMM_SMEM, st>>>(
+                        ds, bl, h->d_tmaps.p, h->d_tmap_of.p, mode, J0, na, h->tma_kmajor, h->d_L.p, h->d_U.p, h->d_D.p);
+                else
+                    k_ldl_update_ldg<<<dim3(gx, B.cnt), 256, 0, st>>>(ds, bl, mode, J0, na, h->d_L.p, h->d_U.p, h->d_D.p);
+                LAUNCH(h);
+            };
             for (int kb = 0; kb < B.maxns; kb += PB) {
                 { FineScope fs(h, Timers::F_DIAG);
-                  k_diag64<<<B.cnt, 256, (size_t)(GSM + PB * (PB + 1)) * sizeof(double), st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p,
-                                                   rp, h->d_nreg.p);
+                  k_piv_diag<<<B.cnt, 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
                   LAUNCH(h); }
                 const int rows_below = B.maxnf - kb - 1;
                 if (rows_below > 0) {
                     FineScope fs(h, Timers::F_ROWS);
-                    k_rows64<<<dim3(nblk(rows_below, GBM), B.cnt), 256, sm64, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p,
-                                                                                     wo, h->d_D.p, h->d_Dinv.p);
+                    k_piv_rows<<<dim3(nblk(rows_below, GBM), B.cnt), 256, smrows, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_Dinv.p);
                     LAUNCH(h);
                 }
+                if (kb + PB < B.maxns) { FineScope fs(h, Timers::F_PANELUPD); launch_update(0, kb); }
             }
             if (h->detail) { h->tm.end(st); h->tm.begin(Timers::SCHUR, st); }
-            {
-                const int T = nblk(B.maxnr, GBM);
-                if (T > 0) {
-                    FineScope fs(h, Timers::F_SCHUR);
-                    k_schur_large<<<dim3(T * (T + 1) / 2, B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_U.p, h->d_D.p);
-                    LAUNCH(h);
-                }
-            }
+            { FineScope fs(h, Timers::F_SCHUR); launch_update(1, 0); }
             if (h->detail) h->tm.end(st);
             FineScope fs(h, Timers::F_FINISH);
             k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_W.p, wo);
@@ -730,7 +798,9 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         ri.resize(nnz);
         for (int64_t i = 0; i < nnz; ++i) ri[i] = rowval[i] - base;
         if (!g_block_hint.empty() && (int64_t)g_block_hint.size() != N) g_block_hint.clear();
-        symbolic_analyze(N, cp.data(), ri.data(), options_from_settings(&st), nullptr, h->S);
+        h->opt = options_from_settings(&st);
+        symbolic_analyze(N, cp.data(), ri.data(), h->opt, nullptr, h->S);
+        h->opt.block_id = nullptr;
         g_block_hint.clear();
         const Symbolic& S = h->S;
         CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -777,18 +847,11 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(h->d_rows.upload(S.rows, s)); CUDA_OK(h->d_rel.upload(S.rel, s));
         CUDA_OK(h->d_child_ptr.upload(S.child_ptr, s)); CUDA_OK(h->d_child_list.upload(S.child_list, s));
         CUDA_OK(h->d_panel_off.upload(S.panel_off, s)); CUDA_OK(h->d_upd_off.upload(S.upd_off, s));
+        CUDA_OK(h->d_ld.upload(S.panel_ld, s));
         CUDA_OK(h->d_front_ptr.upload(S.front_ptr, s)); CUDA_OK(h->d_asm_base.upload(S.asm_base, s));
         CUDA_OK(h->d_asm_colptr.upload(S.asm_colptr, s)); CUDA_OK(h->d_asm_src.upload(S.asm_src, s));
         CUDA_OK(h->d_asm_child.upload(S.asm_child, s));
         // ---- level plans (+ workspace sized for them)
-        h->use_panel_kernel = !(getenv("CB200_NO_PANEL") && getenv("CB200_NO_PANEL")[0] == '1');
-        auto env_int = [](const char* name, int dflt, int lo, int hi) {
-            const char* e = getenv(name);
-            return e ? std::max(lo, std::min(hi, atoi(e))) : dflt;
-        };
-        h->panel_min_nf = env_int("CB200_PANEL_MIN_NF", 64, 16, 152);
-        h->panel_max_nf = env_int("CB200_PANEL_MAX_NF", 152, 16, 152);
-        h->small_max_nf = env_int("CB200_SMALL_MAX_NF", 152, 16, 152);
         { int rcp = build_plans(h); if (rcp) return rcp; }
         // ---- numeric storage
         CUDA_OK(h->d_L.alloc((size_t)S.panel_off.back()));
@@ -812,10 +875,10 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (64 * 64 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_factor_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (32 * 32 + SB * SB) * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_diag64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (GSM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_rows64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (GSM + 2 * PB * (PB + 1)) * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_piv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * PB * (PB + 1)) * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_GEMM_SMEM));
+        { int rct = build_tensor_maps(h); if (rct) return rct; }
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); return -4; }
@@ -1268,9 +1331,10 @@ int32_t cb200_set_detail(cb200_handle* h, int32_t level) { h->detail = level < 0
 static const char* const kFineNames[Timers::NFINE] = {
     "factor_small_nf16", "factor_small_nf32", "factor_small_nf64", "factor_small_nf96", "factor_small_nf128",
     "factor_small_nf152", "factor_panel_c0", "factor_panel_c1", "factor_panel_c2", "factor_panel_c3",
-    "zero_update_blocks", "assemble_large", "diag64", "rows64", "schur_large", "finish_large", "factor_prologue",
+    "zero_update_blocks", "assemble_large", "piv_diag", "piv_rows", "schur_gemm", "finish_large", "factor_prologue",
     "fwd_leaf", "fwd_sub", "fwd_warp", "fwd_cta", "fwd_big_assemble", "fwd_big_tri", "fwd_big_gemv",
-    "bwd_leaf", "bwd_sub", "bwd_warp", "bwd_cta", "bwd_big_gemvT", "bwd_big_tri", "permute_vectors", "nccl"};
+    "bwd_leaf", "bwd_sub", "bwd_warp", "bwd_cta", "bwd_big_gemvT", "bwd_big_tri", "permute_vectors", "nccl",
+    "panel_update"};
 
 int32_t cb200_get_fine_timers(cb200_handle* h, double* out_ms, int32_t len) {
     for (int i = 0; i < len && i < Timers::NFINE; ++i) out_ms[i] = h->tm.ms[Timers::NCOARSE + i];

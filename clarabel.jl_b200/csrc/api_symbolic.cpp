@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -23,6 +24,15 @@ SymbolicOptions options_from_settings(const cb200_settings* st) {
             o.relax_small = (int32_t)a; o.relax_z1 = b; o.relax_z2 = c; o.relax_z3 = d; o.max_width = (int32_t)w;
         }
     }
+    auto env_int = [](const char* name, int dflt, int lo, int hi) {
+        const char* e = getenv(name);
+        return e ? std::max(lo, std::min(hi, atoi(e))) : dflt;
+    };
+    o.collapse_nf = env_int("CB200_COLLAPSE_NF", 32, 0, 64);
+    o.use_panel_kernel = !(getenv("CB200_NO_PANEL") && getenv("CB200_NO_PANEL")[0] == '1');
+    o.panel_min_nf = env_int("CB200_PANEL_MIN_NF", 64, 16, 152);
+    o.panel_max_nf = env_int("CB200_PANEL_MAX_NF", 152, 16, 152);
+    o.small_max_nf = env_int("CB200_SMALL_MAX_NF", 152, 16, 152);
     if (st) {
         o.ordering = st->ordering;
         if (st->amd_dense_scale > 0) o.dense_scale = st->amd_dense_scale;
@@ -121,6 +131,7 @@ int32_t cb200_symbolic_get(const cb200_symbolic* s, int32_t which, int64_t* out,
         case 6: return copy_out(S.panel_off, out, len); case 7: return copy_out(S.upd_off, out, len);
         case 8: return copy_out(S.a_map, out, len);     case 9: return copy_out(S.sn_level, out, len);
         case 10: return copy_out(S.child_ptr, out, len); case 11: return copy_out(S.child_list, out, len);
+        case 12: return copy_out(S.panel_ld, out, len);
     }
     cb200::set_error("cb200_symbolic_get: bad selector"); return -2;
 }

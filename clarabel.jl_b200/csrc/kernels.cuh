@@ -5,8 +5,8 @@
 //   G2  PSD skron                         k_psd_rrt, k_psd_skron
 //   G3  static regularisation             k_diag_absmax, k_compute_eps, k_shift_diag
 //   G4  small-front LDL' (shared memory)  k_factor_small (nf <= 64), k_factor_panel (64 < nf <= 152)
-//   G5  large-front blocked LDL'          k_diag64, k_rows64, k_schur_large, k_finish_large
-//                                         (64 x 64 GEMM tile on the FP64 tensor-core path: DMMA m8n8k4)
+//   G5  large-front blocked LDL'          k_piv_diag, k_piv_rows, k_ldl_update_tma (TMA-fed 128 x 128 DMMA GEMM),
+//                                         k_ldl_update_ldg (fallback), k_finish_large
 //   G6  extend-add                        fused in G4 ; k_assemble_large ; k_assemble_atomic
 //   G7  multifrontal triangular solves    k_fwd_{leaf,sub,warp,cta}, k_bwd_*, k_big_{asm,tri,gemv}_*,
 //                                         k_pack_perm, k_unpack_perm
@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace cb200 {
 
@@ -26,6 +27,7 @@ struct DevSym {                 // device copies of the Symbolic arrays
     const int32_t* child_ptr;
     const int32_t* child_list;
     const int64_t* panel_off;
+    const int32_t* ld;          // [nsuper] leading dimension of each panel (>= nf; padded for large fronts)
     const int64_t* upd_off;
     const int8_t*  dsign;       // [N] permuted pivot signs
     const int64_t* front_ptr;   // destination-owner assembly maps (symbolic.h)
@@ -365,13 +367,14 @@ k_assemble_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict
     const int ns = S.sn_first[s + 1] - f;
     const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int d = blockIdx.x * ASM_CW + wid;
     if (d >= nf) return;
     if (S.child_ptr[s + 1] - S.child_ptr[s] > MANY_CHILDREN) return;     // k_assemble_atomic
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
-    double* dst = d < ns ? Lp + (int64_t)d * nf : Us + (int64_t)(d - ns) * nr - ns;
+    double* dst = d < ns ? Lp + (int64_t)d * ld : Us + (int64_t)(d - ns) * nr - ns;
     const int32_t* cp = S.asm_colptr + S.front_ptr[s];
     const int64_t base = S.asm_base[s];
     for (int e = cp[d]; e < cp[d + 1]; ++e) {
@@ -400,6 +403,7 @@ k_assemble_atomic(DevSym S, int s, double* __restrict__ Lst, double* __restrict_
     const int ns = S.sn_first[s + 1] - f;
     const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
     const int64_t rp0 = S.rows_ptr[c];
@@ -410,30 +414,33 @@ k_assemble_atomic(DevSym S, int s, double* __restrict__ Lst, double* __restrict_
         const int i = e % nrc, j = e / nrc;
         if (i < j) continue;
         const int dj = relc[j], di = relc[i];
-        double* dst = dj < ns ? Lp + (int64_t)dj * nf + di : Us + (int64_t)(dj - ns) * nr + (di - ns);
+        double* dst = dj < ns ? Lp + (int64_t)dj * ld + di : Us + (int64_t)(dj - ns) * nr + (di - ns);
         atomicAdd(dst, Uc[e]);
     }
 }
 
 // ------------------------------------------------------------------ G5 large fronts, blocked
-// Left-looking blocked LDL' in global memory, batched over the large fronts of a level:
-//   for each pivot block J (64 columns): k_diag64 (GEMM update + LDL' + inverse of the diagonal
-//       block) and k_rows64 (GEMM update of the rows below, then multiply by inv(L_JJ)' D_J^-1)
-//   k_schur_large       : F22 -= L21 * D * L21'   one GEMM with K = ns  (the Schur complement)
-//   k_finish_large      : move the parked inverted diagonal blocks into the panel
-// The trailing matrix is read and written once (big-K GEMMs), not once per pivot block.
+// Right-looking blocked LDL' in global memory, batched over the large fronts of a level.  Panels
+// of large fronts have a padded leading dimension ld (multiple of 8 doubles) so that TMA can
+// address them.  Per pivot block J (PB = 64 columns) three launches:
+//   k_piv_diag            one CTA per front: LDL' of the (already updated) 64 x 64 diagonal block with
+//                         the sign-based dynamic regularisation, inverse of its unit-lower factor
+//   k_piv_rows            CTA per 64-row tile below: L[rows,J] = F[rows,J] inv(L_JJ)' D_J^-1
+//   k_ldl_update (mode 0) F[r,c] -= L[r,J] D_J L[c,J]'  for the remaining PANEL columns c, r >= c (K = 64)
+// and once per front
+//   k_ldl_update (mode 1) F22 -= L21 D L21'   (K = ns: the Schur complement into the update block)
+//   k_finish_large        move the parked inverted diagonal blocks into the panel
+// No CTA ever runs a deep GEMM on its own (the old left-looking k_diag64 did: K = J0 for a 64 x 64
+// tile); the trailing update block is read and written once (big-K GEMM).
+// k_ldl_update exists in two versions:
+//   k_ldl_update_tma   128 x 128 CTA tile, operands brought in by TMA (cp.async.bulk.tensor.3d) through a
+//                      4-stage mbarrier ring by one producer warp, 8 consumer warps on the FP64
+//                      tensor-core path (DMMA m8n8k4; tcgen05 has no f64 kind)
+//   k_ldl_update_ldg   64 x 64 tile, LDG -> registers -> STS double buffering (fallback when the
+//                      driver cannot encode tensor maps, and the reference for A/B comparisons)
 constexpr int GBM = 64, GBK = 16;
+constexpr int PB = 64;
 
-// Front-local element address: column g < ns lives in the panel, otherwise in the update block.
-__device__ __forceinline__ double* front_col(double* Lp, double* Us, int ns, int nr, int nf, int g) {
-    return g < ns ? Lp + (int64_t)g * nf : Us + (int64_t)(g - ns) * nr - ns;
-}
-
-// acc (4 x 4 per thread, rows tx*4+a, cols ty*4+c) = sum_{k in [k0,k1)} L[rowA0+i, k] D[k] L[rowB0+j, k]
-// 64 x 64 tile, 256 threads = 8 warps (2 x 4), each warp 32 x 16 of the tile as 4 x 2 FP64
-// tensor-core fragments: mma.sync.aligned.m8n8k4.f64 (DMMA - the FP64 path of the tensor cores;
-// tcgen05 has no f64 kind).  K-step 16 (4 mma k-steps), register prefetch of the next K-slab,
-// double-buffered shared memory with a 72-double row stride (conflict-free fragment loads).
 constexpr int GLD = 72;                        // smem row stride (doubles)
 constexpr int GSM = 2 * 2 * GBK * GLD;         // doubles of shared memory used by the tile routine
 
@@ -442,7 +449,40 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int nf,
+// Tile decode shared by both GEMM versions.  Updated elements: c_lo <= col < c_hi, col <= row < nf
+// with k in [k0, k1).  Tiles of size T are anchored at front-local index 0.
+//   mode 0 (panel step at pivot block J0): k = [J0, min(J0+PB, ns)), cols (k1, ns);  grid.x = nb * na,
+//          tile (tj0 + b, tj0 + b + a) for b = x / na, a = x % na
+//   mode 1 (Schur): k = [0, ns), cols [ns, nf);  grid.x = T (T + 1) / 2 triangular over tiles >= tj0
+struct UpdTile { int k0, k1, c_lo, c_hi, ti, tj; bool valid; };
+template <int T>
+__device__ __forceinline__ UpdTile decode_update_tile(int mode, int J0, int na, int ns, int nf) {
+    UpdTile u; u.valid = false;
+    if (mode == 0) {
+        if (J0 >= ns) return u;
+        u.k0 = J0; u.k1 = min(J0 + PB, ns); u.c_lo = u.k1; u.c_hi = ns;
+        if (u.c_lo >= u.c_hi) return u;
+        const int tj0 = u.c_lo / T;
+        u.tj = tj0 + (int)blockIdx.x / na; u.ti = u.tj + (int)blockIdx.x % na;
+    } else {
+        if (nf == ns) return u;
+        u.k0 = 0; u.k1 = ns; u.c_lo = ns; u.c_hi = nf;
+        const int tj0 = u.c_lo / T;
+        const int idx = blockIdx.x;
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= idx) ++a;
+        while (a * (a + 1) / 2 > idx) --a;
+        u.ti = tj0 + a; u.tj = tj0 + idx - a * (a + 1) / 2;
+    }
+    u.valid = (u.tj * T < u.c_hi) && (u.ti * T < nf);
+    return u;
+}
+
+// acc (4 x 4 per thread, rows tx*4+a, cols ty*4+c) = sum_{k in [k0,k1)} L[rowA0+i, k] D[k] L[rowB0+j, k]
+// 64 x 64 tile, 256 threads = 8 warps (2 x 4), each warp 32 x 16 of the tile as 4 x 2 DMMA fragments.
+// K-step 16, register prefetch of the next K-slab, double-buffered shared memory with a 72-double
+// row stride (conflict-free fragment loads).
+__device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int ld, int nf,
                                               const double* __restrict__ Dv, int rowA0, int rowB0,
                                               int k0, int k1, double (&acc)[4][4], double* gsm) {
     const int tid = threadIdx.x;
@@ -462,15 +502,14 @@ __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) { cf[i][j][0] = 0.0; cf[i][j][1] = 0.0; }
-    // loader mapping: element e = tid + 256 u ; row = e % 64, k = e / 64  (4 of A, 4 of B per thread)
     double ra[4], rb[4];
     auto gload = [&](int kk) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + 256 * u, r = e & 63, k = kk + (e >> 6);
             const int ga = rowA0 + r, gb = rowB0 + r;
-            ra[u] = (k < k1 && ga < nf) ? Lp[(int64_t)k * nf + ga] : 0.0;
-            rb[u] = (k < k1 && gb < nf) ? Lp[(int64_t)k * nf + gb] * Dv[k] : 0.0;
+            ra[u] = (k < k1 && ga < nf) ? Lp[(int64_t)k * ld + ga] : 0.0;
+            rb[u] = (k < k1 && gb < nf) ? Lp[(int64_t)k * ld + gb] * Dv[k] : 0.0;
         }
     };
     auto sstore = [&](int buf) {
@@ -506,7 +545,6 @@ __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int
         __syncthreads();
         buf ^= 1;
     }
-    // redistribute the fragments through shared memory to the (tx, ty) 4 x 4 ownership the callers use
     double* Cs = gsm;                           // 64 x 65 doubles, aliases the operand buffers
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -524,46 +562,194 @@ __device__ __forceinline__ void ldl_gemm_tile(const double* __restrict__ Lp, int
     __syncthreads();
 }
 
-// Pivot block J (PB = 64 columns) of the large fronts of a level, two launches:
-//   k_diag64 : one CTA per front.  Dblk = F[J,J] - L[J,0:J] D L[J,0:J]' (GEMM), LDL' of the 64x64
-//              block by one warp (sign-based dynamic regularisation), inverse of its unit-lower
-//              factor.  Parks [inv(L_JJ) strictly lower ; d on the diagonal] in the workspace.
-//   k_rows64 : CTA per 64-row tile below the block.  T = F[rows,J] - L[rows,0:J] D L[J,0:J]'
-//              (GEMM, K = J), then L[rows,J] = T * inv(L_JJ)' * D_J^-1 (64x64x64 from smem).
-constexpr int PB = 64;
-
 __global__ void __launch_bounds__(256)
-k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __restrict__ Lst,
-         double* __restrict__ Wst, const int64_t* __restrict__ woff, double* __restrict__ D,
-         double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
-    extern __shared__ double smem[];
-    double* gsm = smem;
-    double* A = smem + GSM;                           // 64 x 65
+k_ldl_update_ldg(DevSym S, const int32_t* __restrict__ batch, int mode, int J0, int na,
+                 double* __restrict__ Lst, double* __restrict__ Ust, const double* __restrict__ D) {
+    __shared__ double gsm[GSM];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    const int ld = S.ld[s];
+    const UpdTile u = decode_update_tile<GBM>(mode, J0, na, ns, nf);
+    if (!u.valid) return;
+    double* Lp = Lst + S.panel_off[s];
+    double acc[4][4];
+    ldl_gemm_tile(Lp, ld, nf, D + f, u.ti * GBM, u.tj * GBM, u.k0, u.k1, acc, gsm);
+    double* Us = Ust + S.upd_off[s];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int col = u.tj * GBM + ty * 4 + c;
+        if (col < u.c_lo || col >= u.c_hi) continue;
+        double* dcol = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = u.ti * GBM + tx * 4 + a;
+            if (row < nf && row >= col) dcol[row] -= acc[a][c];
+        }
+    }
+}
+
+// ---- TMA-fed version -------------------------------------------------------------------------
+constexpr int TB = 128;                         // CTA tile (rows and columns)
+constexpr int TK = 16;                          // k-slab per pipeline stage
+constexpr int TSTAGES = 4;
+constexpr int TMA_THREADS = 288;                // 8 consumer warps + 1 producer warp
+constexpr int TTILE = TB * TK;                  // doubles per operand per stage (16 KB)
+constexpr size_t TMA_GEMM_SMEM = (size_t)TSTAGES * 2 * TTILE * sizeof(double) + 2 * TSTAGES * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load: box -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// The tensor map of a panel views it as (8 rows, k, row-groups of 8) with strides (8 B, ld*8 B, 64 B):
+// a box (8, TK, TB/8) lands in shared memory as [row-group][k][8 rows], so the four k-lanes of a DMMA
+// fragment load read 32 consecutive doubles (conflict-free).  If the driver rejects that dimension
+// order the natural one (8 rows, row-groups, k) is used: layout [k][row-group][8], strides passed in
+// (sk, srg) - same kernel, 4-way bank conflicts on the fragment loads.
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap* __restrict__ maps,
+                 const int32_t* __restrict__ map_of, int mode, int J0, int na, int kmajor,
+                 double* __restrict__ Lst, double* __restrict__ Ust, const double* __restrict__ D) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    const int s = batch[blockIdx.y];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    const int ld = S.ld[s];
+    const UpdTile u = decode_update_tile<TB>(mode, J0, na, ns, nf);
+    if (!u.valid) return;
+    double* sA = reinterpret_cast<double*>(tma_smem);
+    double* sB = sA + TSTAGES * TTILE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + TSTAGES * TTILE);
+    uint64_t* empty = full + TSTAGES;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nk = (u.k1 - u.k0 + TK - 1) / TK;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < TSTAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (wid == 8) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            const CUtensorMap* tm = maps + map_of[s];
+            for (int it = 0; it < nk; ++it) {
+                const int st = it % TSTAGES;
+                const uint32_t ph = (uint32_t)(it / TSTAGES) & 1u;
+                mbar_wait(empty + st, ph ^ 1u);                      // slot free (passes at once on a fresh barrier)
+                mbar_expect_tx(full + st, 2u * TTILE * (uint32_t)sizeof(double));
+                const int kc = u.k0 + it * TK;
+                if (kmajor) {
+                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, kc, u.ti * (TB / 8));
+                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, kc, u.tj * (TB / 8));
+                } else {
+                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, u.ti * (TB / 8), kc);
+                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, u.tj * (TB / 8), kc);
+                }
+            }
+        }
+        return;
+    }
+    // ===== 8 consumer warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA fragments =====
+    const int sk = kmajor ? 8 : TB, srg = kmajor ? TK * 8 : 8;      // strides (doubles) of k and of a row-group
+    const int wm = (wid & 1) * 64, wn = (wid >> 1) * 32;
+    const int g = lane >> 2, t = lane & 3;
+    const double* Dv = D + f;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int it = 0; it < nk; ++it) {
+        const int st = it % TSTAGES;
+        const uint32_t ph = (uint32_t)(it / TSTAGES) & 1u;
+        double dv[4];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) { const int k = u.k0 + it * TK + k4 * 4 + t; dv[k4] = (k < u.k1) ? Dv[k] : 0.0; }
+        mbar_wait(full + st, ph);
+        const double* A = sA + st * TTILE + (wm / 8) * srg + g;
+        const double* B = sB + st * TTILE + (wn / 8) * srg + g;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const int ko = (k4 * 4 + t) * sk;
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = A[i * srg + ko];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = B[j * srg + ko] * dv[k4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+    }
+    // ===== epilogue: subtract into the panel (col < ns) or the update block =====
+    double* Lp = Lst + S.panel_off[s];
+    double* Us = Ust + S.upd_off[s];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = u.tj * TB + wn + 8 * j + 2 * t + e;
+            if (col < u.c_lo || col >= u.c_hi) continue;
+            double* dcol = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = u.ti * TB + wm + 8 * i + g;
+                if (row < nf && row >= col) dcol[row] -= acc[i][j][e];
+            }
+        }
+}
+
+// Pivot block J of the large fronts of a level: LDL' + inverse of the 64 x 64 diagonal block.
+// Parks [inv(L_JJ) strictly lower ; d on the diagonal] in the workspace.  One CTA per front.
+__global__ void __launch_bounds__(256)
+k_piv_diag(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __restrict__ Lst,
+           double* __restrict__ Wst, const int64_t* __restrict__ woff, double* __restrict__ D,
+           double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
+    __shared__ double A[PB * (PB + 1)];               // column-major, ld = 65
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
     if (J0 >= ns) return;
-    const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int ld = S.ld[s];
     const int nb = min(PB, ns - J0);
     const double* Lp = Lst + S.panel_off[s];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double acc[4][4];
-    ldl_gemm_tile(Lp, nf, D + f, J0, J0, 0, J0, acc, gsm);
-    if (J0 == 0) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int i = e & (PB - 1), j = e >> 6;
+        double v = 0.0;
+        if (i < nb && j < nb && i >= j) v = Lp[(int64_t)(J0 + j) * ld + J0 + i];
+        A[i + j * (PB + 1)] = v;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = tx * 4 + a, j = ty * 4 + c;
-            double v = 0.0;
-            if (i < nb && j < nb && i >= j) v = Lp[(int64_t)(J0 + j) * nf + J0 + i] - acc[a][c];
-            A[i + j * (PB + 1)] = v;                    // column-major, ld = 65
-        }
     __syncthreads();
     // ---- blocked LDL' of the 64 x 64 block in 4 panels of 16 columns.  Per panel: the 16 x 16
     // diagonal sub-block is factored by warp 0 in registers (row per lane, shuffles broadcast the
@@ -689,40 +875,31 @@ k_diag64(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __re
     }
 }
 
+// L[rows, J] = F[rows, J] * inv(L_JJ)' * D_J^-1 for a 64-row tile below the pivot block.
+// grid (row tiles, nbatch), dynamic smem 2 * 64 * 65 doubles.
 __global__ void __launch_bounds__(256)
-k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict__ Lst,
-         const double* __restrict__ Wst, const int64_t* __restrict__ woff,
-         const double* __restrict__ D, const double* __restrict__ Dinv) {
+k_piv_rows(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict__ Lst,
+           const double* __restrict__ Wst, const int64_t* __restrict__ woff,
+           const double* __restrict__ Dinv) {
     extern __shared__ double smem[];
-    double* gsm = smem;
-    double* Ts = smem + GSM;                          // T: 64 rows x 65 (k index fastest -> [i][k])
+    double* Ts = smem;                                // T: 64 rows x 65 (k index fastest -> [i][k])
     double* Ms = Ts + PB * (PB + 1);                  // M[k][j], 64 x 65
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
     if (J0 >= ns) return;
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int ld = S.ld[s];
     const int nb = min(PB, ns - J0);
     const int r0 = J0 + nb + blockIdx.x * GBM;
     if (r0 >= nf) return;
     double* Lp = Lst + S.panel_off[s];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double acc[4][4];
-    ldl_gemm_tile(Lp, nf, D + f, r0, J0, 0, J0, acc, gsm);
-    if (J0 == 0) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int i = e & (PB - 1), k = e >> 6;
+        const int gr = r0 + i;
+        Ts[i * (PB + 1) + k] = (gr < nf && k < nb) ? Lp[(int64_t)(J0 + k) * ld + gr] : 0.0;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = tx * 4 + a, k = ty * 4 + c;
-            const int gr = r0 + i;
-            Ts[i * (PB + 1) + k] = (gr < nf && k < nb) ? Lp[(int64_t)(J0 + k) * nf + gr] - acc[a][c] : 0.0;
-        }
     const double* Wd = Wst + woff[blockIdx.y] + (int64_t)(J0 / PB) * (PB * PB);
     for (int e = tid; e < PB * PB; e += 256) {
         const int jj = e % PB, kk = e / PB;          // Wd[jj + kk*PB] = inv(L_JJ)[jj][kk] (jj > kk)
@@ -756,46 +933,11 @@ k_rows64(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restrict
     for (int c = 0; c < 4; ++c) {
         const int j = ty * 4 + c;
         if (j >= nb) continue;
-        double* col = Lp + (int64_t)(J0 + j) * nf;
+        double* col = Lp + (int64_t)(J0 + j) * ld;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int gr = r0 + tx * 4 + a;
             if (gr < nf) col[gr] = out[a][c];
-        }
-    }
-}
-
-// grid (tile pairs ti >= tj over the nr x nr update block, nbatch): F22 -= L21 D L21'
-__global__ void __launch_bounds__(256)
-k_schur_large(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
-              double* __restrict__ Ust, const double* __restrict__ D) {
-    __shared__ double gsm[GSM];
-    const int s = batch[blockIdx.y];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int nf = ns + nr;
-    const int T = (nr + GBM - 1) / GBM;
-    int idx = blockIdx.x;
-    if (idx >= T * (T + 1) / 2) return;
-    int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
-    while (ti * (ti + 1) / 2 > idx) --ti;
-    const int tj = idx - ti * (ti + 1) / 2;
-    const double* Lp = Lst + S.panel_off[s];
-    double acc[4][4];
-    ldl_gemm_tile(Lp, nf, D + f, ns + ti * GBM, ns + tj * GBM, 0, ns, acc, gsm);
-    double* Us = Ust + S.upd_off[s];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int gj = tj * GBM + ty * 4 + c;
-        if (gj >= nr) continue;
-        double* col = Us + (int64_t)gj * nr;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int gi = ti * GBM + tx * 4 + a;
-            if (gi < nr && gi >= gj) col[gi] -= acc[a][c];
         }
     }
 }
@@ -812,12 +954,13 @@ k_finish_large(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
     const int kb = blockIdx.x * PB;
     if (kb >= ns) return;
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int ld = S.ld[s];
     const int sb = min(PB, ns - kb);
-    double* Lp = Lst + S.panel_off[s] + (int64_t)kb * nf + kb;
+    double* Lp = Lst + S.panel_off[s] + (int64_t)kb * ld + kb;
     const double* Wd = Wst + woff[blockIdx.y] + (int64_t)blockIdx.x * (PB * PB);
     for (int e = threadIdx.x; e < PB * PB; e += 256) {
         const int i = e % PB, j = e / PB;
-        if (i < sb && j < sb && i >= j) Lp[i + (int64_t)j * nf] = Wd[e];
+        if (i < sb && j < sb && i >= j) Lp[i + (int64_t)j * ld] = Wd[e];
     }
 }
 
@@ -995,6 +1138,7 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     const int64_t rp = S.rows_ptr[s];
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     {
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
         const int64_t base = S.asm_base[s];
@@ -1009,14 +1153,14 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     double xi = 0.0;
     if (lane < ns) {
         xi = w[lane];
-        for (int j = 0; j < lane; ++j) xi += Lp[(int64_t)j * nf + lane] * w[j];
+        for (int j = 0; j < lane; ++j) xi += Lp[(int64_t)j * ld + lane] * w[j];
     }
     __syncwarp();
     if (lane < ns) { w[lane] = xi; y[f + lane] = xi; }
     __syncwarp();
     for (int r = ns + lane; r < nf; r += 32) {
         double acc = w[r];
-        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * nf + r] * w[j];
+        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * ld + r] * w[j];
         uvec[rp + r - ns] = acc;
     }
 }
@@ -1035,13 +1179,14 @@ k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     const int64_t rp = S.rows_ptr[s];
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     for (int i = lane; i < nf; i += 32) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
     __syncwarp();
     const double* Lp = Lst + S.panel_off[s];
     // t_j = w_j - sum_r L[r,j] w_r  (lane j keeps t_j)
     double tj = 0.0;
     for (int j = 0; j < ns; ++j) {
-        const double* cj = Lp + (int64_t)j * nf;
+        const double* cj = Lp + (int64_t)j * ld;
         double acc = 0.0;
         for (int r = ns + lane; r < nf; r += 32) acc += cj[r] * w[r];
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1051,7 +1196,7 @@ k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     double xj = tj;
     for (int i = 1; i < ns; ++i) {
         const double ti = __shfl_sync(0xffffffffu, tj, i);
-        if (lane < i && lane < ns) xj += Lp[(int64_t)lane * nf + i] * ti;
+        if (lane < i && lane < ns) xj += Lp[(int64_t)lane * ld + i] * ti;
     }
     if (lane < ns) y[f + lane] = xj;
 }
@@ -1148,6 +1293,7 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
     const int64_t rp = S.rows_ptr[s];
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     const int tid = threadIdx.x;
     {
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
@@ -1166,7 +1312,7 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         {
             const int i = tid & 63, qd = tid >> 6;
             double acc = 0.0;
-            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * nf + kb + i, nf, i, qd, w + kb);
+            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * ld + kb + i, ld, i, qd, w + kb);
             part[qd][i] = acc;
         }
         __syncthreads();
@@ -1177,8 +1323,8 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         __syncthreads();
         if (tid < sb) w[kb + tid] = xs[tid];
         // rows below the block
-        const double* blk = Lp + (int64_t)kb * nf;
-        for (int r = kb + sb + tid; r < nf; r += 256) w[r] -= row_dot64(blk + r, nf, sb, xs);
+        const double* blk = Lp + (int64_t)kb * ld;
+        for (int r = kb + sb + tid; r < nf; r += 256) w[r] -= row_dot64(blk + r, ld, sb, xs);
         __syncthreads();
     }
     for (int i = tid; i < nf; i += 256) {
@@ -1197,6 +1343,7 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
     const int64_t rp = S.rows_ptr[s];
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
+    const int ld = S.ld[s];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < nf; i += 256) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
     __syncthreads();
@@ -1210,7 +1357,7 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
             const int j0 = wid * 8;
             if (j0 < sb) {
                 double o8[8];
-                cols8_dot(Lp + (int64_t)(kb + j0) * nf, nf, min(8, sb - j0), kb + sb, nf, w, lane, o8);
+                cols8_dot(Lp + (int64_t)(kb + j0) * ld, ld, min(8, sb - j0), kb + sb, nf, w, lane, o8);
                 if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kb + j0 + lane] - o8[lane];
             }
         }
@@ -1224,7 +1371,7 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
                     const int j = j0 + u;
                     double v0 = 0.0, v1 = 0.0;
                     if (j < sb) {
-                        const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
+                        const double* cj = Lp + (int64_t)(kb + j) * ld + kb;
                         const int i0 = lane, i1 = lane + 32;
                         if (i0 > j && i0 < sb) v0 = cj[i0] * ts[i0];
                         if (i1 > j && i1 < sb) v1 = cj[i1] * ts[i1];
@@ -1293,6 +1440,7 @@ k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double*
     if (kb0 >= ns) return;
     const int wp = min(WP, ns - kb0);
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int ld = S.ld[s];
     const int tid = threadIdx.x;
     if (tid < wp) w[tid] = y[f + kb0 + tid];
     __syncthreads();
@@ -1303,15 +1451,15 @@ k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double*
         {
             const int i = tid & 63, qd = tid >> 6;
             double acc = 0.0;
-            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * nf + kb + i, nf, i, qd, w + kk);
+            if (i < sb) acc = diag_row_dot(Lp + (int64_t)kb * ld + kb + i, ld, i, qd, w + kk);
             part[qd][i] = acc;
         }
         __syncthreads();
         if (tid < sb) xs[tid] = w[kk + tid] + part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
         __syncthreads();
         if (tid < sb) w[kk + tid] = xs[tid];
-        const double* blk = Lp + (int64_t)kb * nf + kb0;       // rows relative to panel start
-        for (int r = kk + sb + tid; r < wp; r += 256) w[r] -= row_dot64(blk + r, nf, sb, xs);
+        const double* blk = Lp + (int64_t)kb * ld + kb0;       // rows relative to panel start
+        for (int r = kk + sb + tid; r < wp; r += 256) w[r] -= row_dot64(blk + r, ld, sb, xs);
         __syncthreads();
     }
     if (tid < wp) y[f + kb0 + tid] = w[tid];
@@ -1333,6 +1481,7 @@ k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double
     const int wp = min(WP, ns - kb0);
     const int64_t rp = S.rows_ptr[s];
     const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
+    const int ld = S.ld[s];
     const int r0 = kb0 + wp + blockIdx.x * BRT;
     if (r0 >= nf) return;
     const int tid = threadIdx.x;
@@ -1342,21 +1491,21 @@ k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double
     const int r = r0 + rl;
     double acc = 0.0;
     if (r < nf) {
-        const double* rowp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r;
+        const double* rowp = Lst + S.panel_off[s] + (int64_t)kb0 * ld + r;
         const int j0 = q * (WP / 4), j1 = min(wp, j0 + WP / 4);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int j = j0;
         for (; j + 16 <= j1; j += 16) {
             double v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * nf];
+            for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * ld];
 #pragma unroll
             for (int u = 0; u < 16; u += 4) {
                 a0 += v[u] * xs[j + u]; a1 += v[u + 1] * xs[j + u + 1];
                 a2 += v[u + 2] * xs[j + u + 2]; a3 += v[u + 3] * xs[j + u + 3];
             }
         }
-        for (; j < j1; ++j) a0 += rowp[(int64_t)j * nf] * xs[j];
+        for (; j < j1; ++j) a0 += rowp[(int64_t)j * ld] * xs[j];
         acc = (a0 + a1) + (a2 + a3);
     }
     red[q][rl] = acc;
@@ -1382,6 +1531,7 @@ k_big_gemvT_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtile
     const int wp = min(WP, ns - kb0);
     const int64_t rp = S.rows_ptr[s];
     const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
+    const int ld = S.ld[s];
     const int r0 = kb0 + wp + blockIdx.x * BRT;
     if (r0 >= nf) return;
     const int nrow = min(BRT, nf - r0);
@@ -1389,13 +1539,13 @@ k_big_gemvT_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtile
     if (tid < nrow) { const int r = r0 + tid; ws[tid] = r < ns ? y[f + r] : y[S.rows[rp + r - ns]]; }
     __syncthreads();
     double* out = partial + ((int64_t)blockIdx.y * maxtiles + blockIdx.x) * WP;
-    const double* Lp = Lst + S.panel_off[s] + (int64_t)kb0 * nf + r0;
+    const double* Lp = Lst + S.panel_off[s] + (int64_t)kb0 * ld + r0;
     for (int j = wid * 4; j < wp; j += 32) {          // 8 warps x 4 columns per pass
         double a[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i = lane; i < nrow; i += 32) {
             const double wv = ws[i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (j + u < wp) a[u] += Lp[(int64_t)(j + u) * nf + i] * wv;
+            for (int u = 0; u < 4; ++u) if (j + u < wp) a[u] += Lp[(int64_t)(j + u) * ld + i] * wv;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -1420,6 +1570,7 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
     if (kb0 >= ns) return;
     const int wp = min(WP, ns - kb0);
     const int nf = ns + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int ld = S.ld[s];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ntiles = (nf - kb0 - wp + BRT - 1) / BRT;
     if (tid < wp) {
@@ -1439,7 +1590,7 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
             const int j0 = wid * 8;
             if (j0 < sb) {
                 double o8[8];
-                cols8_dot(Lp + (int64_t)(kb + j0) * nf + kb0, nf, min(8, sb - j0), kk + sb, wp, w, lane, o8);
+                cols8_dot(Lp + (int64_t)(kb + j0) * ld + kb0, ld, min(8, sb - j0), kk + sb, wp, w, lane, o8);
                 if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kk + j0 + lane] - o8[lane];
             }
         }
@@ -1453,7 +1604,7 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
                     const int j = j0 + u;
                     double v0 = 0.0, v1 = 0.0;
                     if (j < sb) {
-                        const double* cj = Lp + (int64_t)(kb + j) * nf + kb;
+                        const double* cj = Lp + (int64_t)(kb + j) * ld + kb;
                         const int i0 = lane, i1 = lane + 32;
                         if (i0 > j && i0 < sb) v0 = cj[i0] * ts[i0];
                         if (i1 > j && i1 < sb) v1 = cj[i1] * ts[i1];
@@ -1556,7 +1707,7 @@ __global__ void k_absmax(const double* __restrict__ v, int64_t n, unsigned long 
 __global__ void k_zero_panels(DevSym S, const int32_t* __restrict__ list, double* __restrict__ Lst) {
     const int s = list[blockIdx.y];
     const int64_t ns = S.sn_first[s + 1] - S.sn_first[s];
-    const int64_t nf = ns + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int64_t nf = S.ld[s];
     double* Lp = Lst + S.panel_off[s];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nf * ns;
          i += (int64_t)gridDim.x * blockDim.x) Lp[i] = 0.0;

@@ -283,7 +283,34 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             below[s] = count[first[s + 1] - 1];      // rows below the supernode's last column
             head[s] = first[s];
         }
+        // 5a. subtree collapse: the bottom of the tree consists of millions of 1-8 column supernodes
+        // (a leaf column and its few neighbours).  A subtree whose merged front is tiny is stored and
+        // processed as ONE dense supernode: the columns of a subtree are contiguous in postorder, the
+        // rows below are those of its root, and the padding zeros cost less than the index traffic
+        // and the per-supernode latency they replace.
+        if (opt.collapse_nf > 0) {
+            std::vector<int32_t> sub_sn(nsn, 1);
+            std::vector<int64_t> sub_cols(nsn), sub_true(nsn);
+            for (int32_t s = 0; s < nsn; ++s) {
+                sub_cols[s] = width[s];
+                int64_t t = 0;
+                for (int32_t j = first[s]; j < first[s + 1]; ++j) t += (int64_t)count[j] + 1;
+                sub_true[s] = t;
+            }
+            for (int32_t s = 0; s < nsn; ++s) if (spar[s] >= 0) {
+                sub_sn[spar[s]] += sub_sn[s]; sub_cols[spar[s]] += sub_cols[s]; sub_true[spar[s]] += sub_true[s];
+            }
+            for (int32_t p = nsn - 1; p >= 0; --p) {
+                if (merged_into[p] >= 0 || sub_sn[p] == 1) continue;
+                const int64_t w = sub_cols[p];
+                if (w + below[p] > opt.collapse_nf || w > opt.max_width) continue;
+                for (int32_t d = p - sub_sn[p] + 1; d < p; ++d) merged_into[d] = p;
+                width[p] = (int32_t)w; head[p] = first[p - sub_sn[p] + 1];
+                zeros[p] = w * (w + 1) / 2 + w * (int64_t)below[p] - sub_true[p];
+            }
+        }
         for (int32_t p = 0; p < nsn; ++p) {
+            if (merged_into[p] >= 0) continue;      // inside a collapsed subtree
             // candidate: the supernode ending right before head[p] whose parent is p
             while (true) {
                 if (head[p] == 0) break;
@@ -384,11 +411,25 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
 
     lap("row structures");
     // ---------------------------------------------------------------- 7. storage + maps
-    S.panel_off.assign(ns2 + 1, 0); S.upd_off.assign(ns2 + 1, 0);
+    S.panel_off.assign(ns2 + 1, 0); S.upd_off.assign(ns2 + 1, 0); S.panel_ld.assign(ns2, 0);
     S.nnzL = 0; S.flops = 0; S.max_front = 0; S.max_width = 0;
+    {
+        int64_t off = 0;
+        for (int32_t s = 0; s < ns2; ++s) {
+            const int64_t w = S.ns(s), nf = w + S.nr(s);
+            int64_t ld = nf;
+            if (front_is_large(opt, (int)nf, (int)w)) {
+                ld = (nf + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
+                off = (off + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
+            }
+            S.panel_ld[s] = (int32_t)ld;
+            S.panel_off[s] = off;
+            off += ld * w;
+        }
+        S.panel_off[ns2] = off;
+    }
     for (int32_t s = 0; s < ns2; ++s) {
         int64_t w = S.ns(s), r = S.nr(s), nf = w + r;
-        S.panel_off[s + 1] = S.panel_off[s] + nf * w;
         S.upd_off[s + 1] = S.upd_off[s] + r * r;
         S.nnzL += w * (w - 1) / 2 + w * r;
         for (int64_t k = 0; k < w; ++k) { double c = (double)(nf - k); S.flops += c * c; }
@@ -455,7 +496,7 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
             int32_t c = std::min(a, b), r = std::max(a, b);
             int32_t s = S.sn_of_col[c];
             int32_t f = S.sn_first[s], l = S.sn_first[s + 1] - 1, w = l - f + 1;
-            int64_t nf = w + S.nr(s);
+            int64_t nf = S.panel_ld[s];
             int64_t lr;
             if (r <= l) lr = r - f;
             else {

@@ -19,9 +19,29 @@ struct SymbolicOptions {
     double relax_z2 = 0.20;      // ... <= 96
     double relax_z3 = 0.05;      // otherwise
     int32_t max_width = 512;     // never merge beyond this many pivot columns
+    int32_t collapse_nf = 32;    // a whole subtree whose merged front (all its columns + the rows below its
+                                 // root) has at most this many rows becomes ONE dense supernode (0 = off)
     const int32_t* block_id = nullptr;   // optional [N]: rows sharing an id >= 0 form a dense cone block
                                          // (clique) that nested dissection must not cut
+    // Size classes of the numeric factorisation (the large-front path pads its panels, so the
+    // symbolic layout has to know which fronts take it): panel-in-smem kernel for
+    // panel_min_nf < nf <= panel_max_nf (if it fits), shared-memory front kernel up to small_max_nf,
+    // large (pivot-block + TMA GEMM) path above.
+    int32_t panel_min_nf = 64, panel_max_nf = 152, small_max_nf = 152;
+    bool use_panel_kernel = true;
 };
+
+// fronts handled by k_factor_panel (panel + scratch in one CTA's shared memory)
+inline bool front_to_panel(const SymbolicOptions& o, int nf, int ns) {
+    return o.use_panel_kernel && nf > o.panel_min_nf && nf <= o.panel_max_nf && ns <= 150 &&
+           ((int64_t)nf * ns + (int64_t)nf * 25) <= 27000;
+}
+// fronts on the large path: their panels are stored with a padded leading dimension (multiple of
+// LD_ALIGN doubles, panel start aligned likewise) so that TMA can address them
+inline bool front_is_large(const SymbolicOptions& o, int nf, int ns) {
+    return nf > o.small_max_nf && !front_to_panel(o, nf, ns);
+}
+constexpr int32_t LD_ALIGN = 8;
 
 struct Symbolic {
     int64_t N = 0, nnzK = 0;
@@ -36,7 +56,9 @@ struct Symbolic {
     std::vector<int32_t> sn_parent; // [nsuper] assembly-tree parent (-1 = root)
     std::vector<int32_t> child_ptr; // [nsuper+1]
     std::vector<int32_t> child_list;
-    std::vector<int64_t> panel_off; // [nsuper+1] doubles; panel s is nf x ns column-major, ld = nf
+    std::vector<int64_t> panel_off; // [nsuper+1] doubles; panel s is nf x ns column-major with leading
+                                    // dimension panel_ld[s] (= nf, or nf rounded up to LD_ALIGN for large fronts)
+    std::vector<int32_t> panel_ld;  // [nsuper]
     std::vector<int64_t> upd_off;   // [nsuper+1] doubles; update block s is nr x nr, ld = nr
     std::vector<int64_t> a_map;     // [nnzK] K nz (original order) -> offset in panel storage
     // Destination-owner form of the extend-add: for front s and front-local index d (column of

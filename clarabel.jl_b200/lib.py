@@ -147,7 +147,7 @@ def cone_block_ids(cones, n, N):
 
 
 _SYM_ARRAYS = ["perm", "sn_first", "rows_ptr", "rows", "rel", "sn_parent", "panel_off", "upd_off",
-               "a_map", "sn_level", "child_ptr", "child_list"]
+               "a_map", "sn_level", "child_ptr", "child_list", "panel_ld"]
 
 
 class Symbolic:
@@ -176,7 +176,10 @@ class Symbolic:
                     panel_off=s["nsuper"] + 1, upd_off=s["nsuper"] + 1, a_map=s["nnzK"],
                     sn_level=s["nsuper"], child_ptr=s["nsuper"] + 1)
         out = {}
-        for i, nm in enumerate(_SYM_ARRAYS[:11]):
+        lens["panel_ld"] = s["nsuper"]
+        for i, nm in enumerate(_SYM_ARRAYS):
+            if nm == "child_list":
+                continue
             a = np.empty(lens[nm], dtype=np.int64)
             check(L.cb200_symbolic_get(self._h, i, _p(a), len(a)), "cb200_symbolic_get")
             out[nm] = a

@@ -4,6 +4,14 @@ kernels use, so symbolic-analysis bugs are caught on the CPU.  Not part of the p
 import numpy as np
 
 
+def panel_view(L, s, sn, nf, ns):
+    """(ns, nf) view (transposed panel) of supernode sn; the panel is column-major with leading
+    dimension panel_ld[sn] (>= nf: large fronts are padded)."""
+    ld = int(s["panel_ld"][sn]) if "panel_ld" in s else nf
+    off = int(s["panel_off"][sn])
+    return L[off:off + ld * ns].reshape(ns, ld)[:, :nf]
+
+
 class MFNumpy:
     def __init__(self, sym):
         """sym: dict of arrays from cb200_symbolic_get (see lib.Symbolic.arrays())."""
@@ -25,7 +33,7 @@ class MFNumpy:
             nr = int(s["rows_ptr"][sn + 1] - s["rows_ptr"][sn])
             nf = ns + nr
             F = np.zeros((nf, nf))
-            F[:, :ns] = L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns].reshape(ns, nf).T
+            F[:, :ns] = panel_view(L, s, sn, nf, ns).T
             for c in s["children"][sn]:
                 nrc = int(s["rows_ptr"][c + 1] - s["rows_ptr"][c])
                 rel = s["rel"][s["rows_ptr"][c]:s["rows_ptr"][c + 1]]
@@ -40,7 +48,7 @@ class MFNumpy:
                 F[k + 1:, k] = col / d
                 F[k + 1:, k + 1:] -= np.tril(np.outer(col, col / d))
                 F[k, k] = 1.0
-            L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns] = F[:, :ns].T.reshape(-1)
+            panel_view(L, s, sn, nf, ns)[:, :] = F[:, :ns].T
             if nr:
                 U[s["upd_off"][sn]:s["upd_off"][sn] + nr * nr] = np.tril(F[ns:, ns:]).T.reshape(-1)
         self.L, self.D = L, D
@@ -55,7 +63,7 @@ class MFNumpy:
             ns = l - f
             rows = s["rows"][s["rows_ptr"][sn]:s["rows_ptr"][sn + 1]]
             nf = ns + len(rows)
-            P = self.L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns].reshape(ns, nf).T
+            P = panel_view(self.L, s, sn, nf, ns).T
             for k in range(ns):
                 y[f + k + 1:l] -= P[k + 1:ns, k] * y[f + k]
             y[rows] -= P[ns:, :] @ y[f:l]
@@ -65,7 +73,7 @@ class MFNumpy:
             ns = l - f
             rows = s["rows"][s["rows_ptr"][sn]:s["rows_ptr"][sn + 1]]
             nf = ns + len(rows)
-            P = self.L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns].reshape(ns, nf).T
+            P = panel_view(self.L, s, sn, nf, ns).T
             y[f:l] -= P[ns:, :].T @ y[rows]
             for k in range(ns - 1, -1, -1):
                 y[f + k] -= P[k + 1:ns, k] @ y[f + k + 1:l]

@@ -5,6 +5,7 @@ places the CUDA path issues NCCL all-reduces (api_cuda.cu: allreduce_fronts / tr
 import os
 import socket
 import numpy as np
+from mf_numpy import panel_view
 import pytest
 import torch
 import torch.distributed as dist
@@ -38,13 +39,13 @@ def _dist_factor_solve(rank, world, sym, owner, top, nzval, Ds, b):
         f, l = int(s["sn_first"][sn]), int(s["sn_first"][sn + 1]); ns = l - f
         nr = int(s["rows_ptr"][sn + 1] - s["rows_ptr"][sn]); geo.append((f, l, ns, nr, ns + nr))
         if rank != 0 and top[sn]:
-            L[s["panel_off"][sn]:s["panel_off"][sn] + (ns + nr) * ns] = 0.0   # orig entries: rank 0 only
+            panel_view(L, s, sn, ns + nr, ns)[:, :] = 0.0   # orig entries: rank 0 only
     for sn in range(nsuper):
         if not mine(sn):
             continue
         f, l, ns, nr, nf = geo[sn]
         F = np.zeros((nf, nf))
-        F[:, :ns] = L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns].reshape(ns, nf).T
+        F[:, :ns] = panel_view(L, s, sn, nf, ns).T
         for c in s["children"][sn]:
             if not active(c):
                 continue
@@ -58,7 +59,7 @@ def _dist_factor_solve(rank, world, sym, owner, top, nzval, Ds, b):
             col = F[k + 1:, k].copy()
             F[k + 1:, k] = col / d
             F[k + 1:, k + 1:] -= np.tril(np.outer(col, col / d))
-        L[s["panel_off"][sn]:s["panel_off"][sn] + nf * ns] = F[:, :ns].T.reshape(-1)
+        panel_view(L, s, sn, nf, ns)[:, :] = F[:, :ns].T
         if nr:
             U[s["upd_off"][sn]:s["upd_off"][sn] + nr * nr] = np.tril(F[ns:, ns:]).T.reshape(-1)
     # ---- solve
@@ -68,7 +69,7 @@ def _dist_factor_solve(rank, world, sym, owner, top, nzval, Ds, b):
         for sn in range(nsuper):
             if top[sn]:
                 y[geo[sn][0]:geo[sn][1]] = 0.0
-    panel = lambda sn: L[s["panel_off"][sn]:s["panel_off"][sn] + geo[sn][4] * geo[sn][2]].reshape(geo[sn][2], geo[sn][4]).T
+    panel = lambda sn: panel_view(L, s, sn, geo[sn][4], geo[sn][2]).T
     for sn in range(nsuper):
         if not mine(sn):
             continue
