@@ -45,7 +45,8 @@ template <class T> struct DevBuf {
 };
 
 struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpanel = 0; bool many_children = false;
-               int32_t schur_t128 = 0, schur_t64 = 0; };      // max over the fronts of the number of update-block tiles per side
+               int32_t schur_t128 = 0, schur_t64 = 0;
+               int32_t src_per_row = 0; };     // max over the fronts of (assembly sources / front rows)      // max over the fronts of the number of update-block tiles per side
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
@@ -55,6 +56,7 @@ constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per s
 
 struct LevelPlan {
     Batch small[NSMALL];
+    Batch w32;                 // nf <= 32: warp-per-front register kernel (k_factor_warp32)
     Batch panel[NPANEL];       // 64 < nf <= 152: panel-in-smem kernel, classes by panel size
     Batch large;
     Batch solve[NSOLVE];
@@ -215,6 +217,22 @@ struct cb200_handle {
     DevBuf<int8_t> d_active, d_keepcol, d_topcolkeep;
     DevBuf<int32_t> d_top_list;
     GraphExec g_factor[2], g_solve;     // CUDA graphs: factor (without/with static reg), solve sweeps
+    // Fork/join streams: the kernel classes of one tree level are independent of each other (small
+    // fronts vs the pivot-block chain of the large fronts; leaf / warp / CTA / big solve classes),
+    // most of them are latency-bound and leave SMs idle, so they run as parallel branches (captured
+    // as such into the CUDA graphs).  CB200_MULTISTREAM=0 serialises them again.
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    bool multi_stream = true;
+    bool use_warp32 = true;            // CB200_NO_WARP32=1: tiny fronts go back to k_factor_small
+    bool ms_on() const { return multi_stream && detail == 0; }
+    void fork(int n) {            // side[0..n) start after everything issued so far on `stream`
+        cudaEventRecord(ev_fork, stream);
+        for (int i = 0; i < n; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
+    }
+    void join(int n) {            // `stream` continues after side[0..n)
+        for (int i = 0; i < n; ++i) { cudaEventRecord(ev_join[i], side[i]); cudaStreamWaitEvent(stream, ev_join[i], 0); }
+    }
     // grow-only device staging for the inner-boundary uploads (update_values!/scale_values!/update_P/A):
     // no cudaMalloc / cudaFree per call and no stream sync for pageable caller buffers
     DevBuf<int64_t> d_stage_idx; DevBuf<double> d_stage_val;
@@ -247,12 +265,12 @@ struct FineScope {
 };
 
 template <int T>
-int launch_small(cb200_handle* h, const Batch& b, int cls, RegParams rp) {
+int launch_small(cb200_handle* h, const Batch& b, int cls, RegParams rp, cudaStream_t st) {
     if (b.cnt == 0) return 0;
     FineScope fs(h, Timers::F_SMALL0 + cls);
     const int sbuf = std::min(SB, b.maxns);
     size_t sm = ((size_t)b.maxnf * b.maxnf + (size_t)sbuf * sbuf) * sizeof(double);
-    k_factor_small<T><<<b.cnt, T, sm, h->stream>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
+    k_factor_small<T><<<b.cnt, T, sm, st>>>(devsym(h), h->d_batches.p + b.off, h->d_L.p,
                                                    h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
     LAUNCH(h);
     return 0;
@@ -260,10 +278,18 @@ int launch_small(cb200_handle* h, const Batch& b, int cls, RegParams rp) {
 
 void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     DevSym ds = devsym(h);
+    // classes of a level are independent: leaf + tiny on side[0], warp on side[1], CTA on side[2], big on the
+    // main stream (fork/join only when a second class has work)
+    const bool big_work = P.solve[3].cnt || P.tops.cnt;
+    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
+    const bool ms = h->ms_on() && nclass > 1;
+    cudaStream_t s_leaf = ms ? h->side[0] : h->stream, s_warp = ms ? h->side[1] : h->stream,
+                 s_cta = ms ? h->side[2] : h->stream;
+    if (ms) h->fork(3);
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
         { FineScope fs(h, Timers::F_FWD_LEAF);
-        k_fwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
+        k_fwd_leaf<<<nblk(b0.cnt, 128), 128, 0, s_leaf>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
                                                              h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
         }
@@ -271,7 +297,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     const Batch& b4 = P.solve[4];
     if (b4.cnt) {
         { FineScope fs(h, Timers::F_FWD_SUB);
-        k_fwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
+        k_fwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, s_leaf>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
                                                                    h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
         }
@@ -279,7 +305,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
         { FineScope fs(h, Timers::F_FWD_WARP);
-        k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
+        k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), s_warp>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
         }
@@ -287,7 +313,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
         { FineScope fs(h, Timers::F_FWD_CTA);
-        k_fwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
+        k_fwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), s_cta>>>(
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
         }
@@ -297,7 +323,9 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
         if (!b3.cnt) continue;
         const int32_t* bl = h->d_batches.p + b3.off;
         { FineScope fs(h, Timers::F_FWD_BIG_ASM);
-        if (b3.many_children)
+        if (b3.src_per_row >= 512)
+            k_big_asm_fwd<256><<<dim3(b3.maxnf, b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
+        else if (b3.many_children)
             k_big_asm_fwd<32><<<dim3(nblk((int64_t)b3.maxnf * 32, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
         else
             k_big_asm_fwd<1><<<dim3(nblk(b3.maxnf, 256), b3.cnt), 256, 0, h->stream>>>(ds, bl, h->d_y.p, h->d_uvec.p);
@@ -332,9 +360,16 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
             }
         }
     }
+    if (ms) h->join(3);
 }
 void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     DevSym ds = devsym(h);
+    const bool big_work = P.solve[3].cnt || P.tops.cnt;
+    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
+    const bool ms = h->ms_on() && nclass > 1;
+    cudaStream_t s_leaf = ms ? h->side[0] : h->stream, s_warp = ms ? h->side[1] : h->stream,
+                 s_cta = ms ? h->side[2] : h->stream;
+    if (ms) h->fork(3);
     for (int pass = 0; pass < 2; ++pass) {
         const Batch& b3 = pass == 0 ? P.tops : P.solve[3];
         if (!b3.cnt) continue;
@@ -358,7 +393,7 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
         { FineScope fs(h, Timers::F_BWD_CTA);
-        k_bwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), h->stream>>>(
+        k_bwd_cta<<<b2.cnt, 256, (size_t)b2.maxnf * sizeof(double), s_cta>>>(
             ds, h->d_batches.p + b2.off, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
         }
@@ -366,7 +401,7 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
         { FineScope fs(h, Timers::F_BWD_WARP);
-        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), h->stream>>>(
+        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), s_warp>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
         }
@@ -374,7 +409,7 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     const Batch& b4 = P.solve[4];
     if (b4.cnt) {
         { FineScope fs(h, Timers::F_BWD_SUB);
-        k_bwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, h->stream>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
+        k_bwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, s_leaf>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
                                                                    h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
         }
@@ -382,11 +417,12 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
         { FineScope fs(h, Timers::F_BWD_LEAF);
-        k_bwd_leaf<<<nblk(b0.cnt, 128), 128, 0, h->stream>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
+        k_bwd_leaf<<<nblk(b0.cnt, 128), 128, 0, s_leaf>>>(ds, h->d_batches.p + b0.off, b0.cnt, h->d_L.p,
                                                              h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
         }
     }
+    if (ms) h->join(3);
 }
 
 
@@ -462,6 +498,7 @@ int build_plans(cb200_handle* h) {
             b.maxnr = std::max(b.maxnr, S.nr(sn));
             b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn) + 25 * nf);      // smem need of k_factor_panel
             if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
+            b.src_per_row = std::max<int32_t>(b.src_per_row, (int32_t)((S.asm_base[sn + 1] - S.asm_base[sn]) / std::max(1, nf)));
             if (large && S.nr(sn) > 0) {
                 b.schur_t128 = std::max(b.schur_t128, (nf - 1) / TB - S.ns(sn) / TB + 1);
                 b.schur_t64 = std::max(b.schur_t64, (nf - 1) / GBM - S.ns(sn) / GBM + 1);
@@ -473,7 +510,7 @@ int build_plans(cb200_handle* h) {
         if (large) { P.wtotal += w; wmax = std::max(wmax, w); }
     };
     for (int lv = 0; lv < S.nlevels; ++lv) {
-        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], pcl[NPANEL], top;
+        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], pcl[NPANEL], top, w32;
         for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
             int32_t sn = S.level_list[q];
             if (h->dist) {
@@ -483,7 +520,8 @@ int build_plans(cb200_handle* h) {
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
             if (h->to_large(nf, S.ns(sn)) || nf > kSmallNf[NSMALL - 1]) c = NSMALL;
-            if (h->to_panel(nf, S.ns(sn))) {
+            if (h->use_warp32 && nf <= 32) w32.push_back(sn);
+            else if (h->to_panel(nf, S.ns(sn))) {
                 int pc = 0; while (nf * S.ns(sn) + 25 * nf > kPanelDoubles[pc]) ++pc;
                 pcl[pc].push_back(sn);
             } else cls[c].push_back(sn);
@@ -496,6 +534,7 @@ int build_plans(cb200_handle* h) {
         LevelPlan& P = h->plan[lv];
         P.wtotal = 0;
         for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
+        add_batch(P.w32, w32, false, P);
         for (int c = 0; c < NPANEL; ++c) add_batch(P.panel[c], pcl[c], false, P);
         add_batch(P.large, cls[NSMALL], true, P);
         for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
@@ -597,19 +636,33 @@ int factor_body(cb200_handle* h, bool static_reg) {
     if (h->detail >= 2) h->tm.end(st);
     for (int lv = 0; lv < S.nlevels; ++lv) {
         const LevelPlan& P = h->plan[lv];
+        bool small_work = false;
+        for (int c = 0; c < NSMALL; ++c) small_work |= P.small[c].cnt != 0;
+        for (int c = 0; c < NPANEL; ++c) small_work |= P.panel[c].cnt != 0;
+        small_work |= P.w32.cnt != 0;
+        // the small-front kernels of a level run beside the pivot-block chain of its large fronts
+        const bool ms = h->ms_on() && small_work && (P.large.cnt || P.topf.cnt);
+        cudaStream_t ss = ms ? h->side[0] : st;
+        if (ms) h->fork(1);
         if (h->detail) h->tm.begin(Timers::SMALL, st);
-        launch_small<32>(h, P.small[0], 0, rp);        // size classes kSmallNf[0..5]
-        launch_small<64>(h, P.small[1], 1, rp);
-        launch_small<128>(h, P.small[2], 2, rp);
-        launch_small<256>(h, P.small[3], 3, rp);
-        launch_small<256>(h, P.small[4], 4, rp);
-        launch_small<256>(h, P.small[5], 5, rp);
+        if (P.w32.cnt) {
+            FineScope fs(h, Timers::F_SMALL0);
+            k_factor_warp32<<<nblk(P.w32.cnt, 8), 256, (size_t)8 * 32 * FW_LD * sizeof(double), ss>>>(
+                ds, h->d_batches.p + P.w32.off, P.w32.cnt, h->d_L.p, h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
+            LAUNCH(h);
+        }
+        launch_small<32>(h, P.small[0], 0, rp, ss);        // size classes kSmallNf[0..5]
+        launch_small<64>(h, P.small[1], 1, rp, ss);
+        launch_small<128>(h, P.small[2], 2, rp, ss);
+        launch_small<256>(h, P.small[3], 3, rp, ss);
+        launch_small<256>(h, P.small[4], 4, rp, ss);
+        launch_small<256>(h, P.small[5], 5, rp, ss);
         for (int c = 0; c < NPANEL; ++c) {
             const Batch& b = P.panel[c];
             if (!b.cnt) continue;
             const size_t sm = (size_t)b.maxpanel * sizeof(double);
             FineScope fs(h, Timers::F_PANEL0 + c);
-            k_factor_panel<<<b.cnt, 256, sm, st>>>(ds, h->d_batches.p + b.off, b.maxpanel, b.maxnf, h->d_L.p, h->d_U.p,
+            k_factor_panel<<<b.cnt, 256, sm, ss>>>(ds, h->d_batches.p + b.off, b.maxpanel, b.maxnf, h->d_L.p, h->d_U.p,
                                                    h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
             LAUNCH(h);
         }
@@ -683,6 +736,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
             k_finish_large<<<dim3(nblk(B.maxns, PB), B.cnt), 256, 0, st>>>(ds, bl, h->d_L.p, h->d_W.p, wo);
             LAUNCH(h);
         }
+        if (ms) h->join(1);
     }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -799,11 +853,51 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         for (int64_t i = 0; i < nnz; ++i) ri[i] = rowval[i] - base;
         if (!g_block_hint.empty() && (int64_t)g_block_hint.size() != N) g_block_hint.clear();
         h->opt = options_from_settings(&st);
+        // ordering = 1 (auto) with dense cone blocks (PSD cones) in K: the blocks are detected here from the
+        // pattern and Dsigns alone - a maximal run of columns of the (-,-) part in which column j holds ALL
+        // earlier columns of the run as rows (a dense triangle; dense SOC blocks have at most 4 columns) - so
+        // that every caller, the Julia shim included, gets the PSD-safe ordering without knowing about it:
+        // coupled variables first, then the blocks by nested dissection of the block graph, or the
+        // AMD-class order when there are only a few blocks (symbolic.cpp / ordering.cpp).
+        std::vector<int32_t> detected;
+        if (h->opt.ordering == 1 && Dsigns && !h->opt.block_id) {
+            std::vector<int32_t> start(N, -1);                 // start[j] = first column of the run j belongs to
+            for (int64_t j = 0; j < N; ++j) {
+                if (Dsigns[j] >= 0) continue;
+                start[j] = (int32_t)j;
+                if (j == 0 || start[j - 1] < 0) continue;
+                const int64_t want = j - start[j - 1];         // rows start[j-1] .. j-1 must all be present
+                int64_t run = 0;
+                for (int64_t p = cp[j + 1] - 1; p >= cp[j]; --p) {
+                    const int64_t r = ri[p];
+                    if (r == j) continue;
+                    if (r == j - 1 - run) ++run; else if (r < j - 1 - run) break;
+                    if (run == want) break;
+                }
+                if (run == want) start[j] = start[j - 1];
+            }
+            detected.assign(N, -1);
+            int32_t nblk_found = 0;
+            for (int64_t j = 0; j < N;) {
+                if (start[j] < 0) { ++j; continue; }
+                int64_t e = j; while (e + 1 < N && start[e + 1] == start[j]) ++e;
+                if (e - j + 1 >= 5) { for (int64_t q = j; q <= e; ++q) detected[q] = nblk_found; ++nblk_found; }
+                j = e + 1;
+            }
+            if (nblk_found > 0) h->opt.block_id = detected.data();
+        }
         symbolic_analyze(N, cp.data(), ri.data(), h->opt, nullptr, h->S);
         h->opt.block_id = nullptr;
         g_block_hint.clear();
         const Symbolic& S = h->S;
         CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            CUDA_OK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+        }
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("CB200_MULTISTREAM")) h->multi_stream = e[0] != '0';
+        if (const char* e = getenv("CB200_NO_WARP32")) h->use_warp32 = e[0] != '1';
         cudaStream_t s = h->stream;
         // ---- K
         std::vector<int32_t> ri32(ri.begin(), ri.end());
@@ -879,6 +973,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_GEMM_SMEM));
         { int rct = build_tensor_maps(h); if (rct) return rct; }
+        CUDA_OK(cudaFuncSetAttribute(k_factor_warp32, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * FW_LD * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); return -4; }
@@ -894,6 +989,11 @@ void cb200_destroy(cb200_handle* h) {
     if (h->stream) { cudaStreamSynchronize(h->stream); }
     if (h->comm && g_nccl.ok) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     cudaStream_t s = h->stream;
+    for (int i = 0; i < 3; ++i) {
+        if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     if (s) cudaStreamDestroy(s);
 }
@@ -1358,10 +1458,10 @@ int32_t cb200_get_stats(const cb200_handle* h, double* out, int32_t len) {
         }
         if (nf * ns >= 65536 && ns > 32) big_bytes += 8.0 * nf * ns;
     }
-    double v[12] = {S.flops, schur, panel_large - schur, (double)S.nnzL, (double)S.nlevels, (double)S.nsuper,
+    double v[14] = {S.flops, schur, panel_large - schur, (double)S.nnzL, (double)S.nlevels, (double)S.nsuper,
                     nlarge, big_bytes, (double)S.upd_total * 8.0, (double)S.panel_off.back() * 8.0,
-                    (double)S.ordering_used, my_flops};
-    for (int i = 0; i < len && i < 12; ++i) out[i] = v[i];
+                    (double)S.ordering_used, my_flops, h->use_tma ? 1.0 : 0.0, (double)h->tma_kmajor};
+    for (int i = 0; i < len && i < 14; ++i) out[i] = v[i];
     return 0;
 }
 

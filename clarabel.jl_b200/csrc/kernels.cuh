@@ -156,6 +156,116 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
     }
 }
 
+// ------------------------------------------------------------------ G4w tiny fronts (nf <= 32): warp per front
+// One warp per front, 8 fronts per CTA, no barrier anywhere.  The front is staged in a per-warp
+// shared-memory tile (coalesced panel read, extend-add through the destination-owner lists: fixed
+// summation order), then lane j takes COLUMN j into registers (a[i] = F[i][j]).  With column
+// ownership the pivot loop runs over a RUNTIME k with only static register indices (a fully
+// unrolled row-ownership version was 20x slower: instruction-cache bound):
+//   LDL'   step k: column k is broadcast by shuffles, d_k gets the sign-based dynamic regularisation
+//          (QDLDL rule), lane j > k applies a[i] -= A[i][k] A[j][k] / d_k to its column
+//   X = inv(L11) in place: acc = -L[:,j]; step k: lanes j < k add L[:,k] X[k][j]  (at step k column k
+//          still holds -L[:,k] untouched, X[k][j] is final)
+// This is the kernel the subtree collapse of the symbolic analysis feeds: ~5e5 fronts on C5.
+constexpr int FW_LD = 33;
+__global__ void __launch_bounds__(256)
+k_factor_warp32(DevSym S, const int32_t* __restrict__ batch, int count, double* __restrict__ Lst,
+                double* __restrict__ Ust, double* __restrict__ D, double* __restrict__ Dinv,
+                RegParams rp, unsigned int* __restrict__ nreg) {
+    extern __shared__ double fw_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 8 + wid;
+    if (idx >= count) return;
+    const int s = batch[idx];
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+    const int nf = ns + nr;
+    double* Lp = Lst + S.panel_off[s];
+    double* F = fw_smem + (size_t)wid * (32 * FW_LD);          // F[i + j*FW_LD], column-major
+    for (int e = lane; e < 32 * FW_LD; e += 32) F[e] = 0.0;
+    __syncwarp();
+    for (int j = 0; j < ns; ++j) if (lane < nf) F[lane + j * FW_LD] = Lp[j * nf + lane];
+    __syncwarp();
+    if (S.child_ptr[s + 1] != S.child_ptr[s]) {
+        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
+        const int64_t base = S.asm_base[s];
+        for (int d = 0; d < nf; ++d) {
+            double* dst = F + d * FW_LD;
+            for (int e = cp[d]; e < cp[d + 1]; ++e) {
+                const int q = S.asm_src[base + e];
+                const int c = S.asm_child[base + e];
+                const int64_t rp0 = S.rows_ptr[c];
+                const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
+                const int jc = (int)(q - rp0);
+                const int32_t* relc = S.rel + rp0;
+                const double* src = Ust + S.upd_off[c] + (int64_t)jc * nrc;
+                for (int i2 = jc + lane; i2 < nrc; i2 += 32) dst[relc[i2]] += src[i2];
+                __syncwarp();
+            }
+        }
+    }
+    double a[32];                                   // column `lane` of the front (rows i >= lane matter)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = (i >= lane) ? F[i + lane * FW_LD] : 0.0;
+    // ---- LDL'
+    unsigned int myreg = 0;
+    double dmine = 1.0, dimine = 1.0;               // lane k keeps d_k and 1/d_k
+    for (int k = 0; k < ns; ++k) {
+        double c[32];
+        double d = 0.0, cj = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            c[i] = __shfl_sync(0xffffffffu, a[i], k);             // A[i][k] (i >= k)
+            if (i == k) d = c[i];
+            if (i == lane) cj = c[i];
+        }
+        const double sg = (double)S.dsign[f + k];
+        if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; if (lane == 0) ++myreg; }
+        const double dinv = 1.0 / d;
+        if (lane > k) {
+            const double wj = cj * dinv;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i >= lane) a[i] -= c[i] * wj;
+        } else if (lane == k) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { if (i > k) a[i] = c[i] * dinv; else if (i == k) a[i] = d; }
+            dmine = d; dimine = dinv;
+        }
+    }
+    if (lane < ns) { D[f + lane] = dmine; Dinv[f + lane] = dimine; }
+    if (lane == 0 && myreg) atomicAdd(nreg, myreg);
+    // ---- X = inv(L11): lane j < ns works on rows j < i < ns of its column; the rows i >= ns (L21) stay
+    if (ns > 1) {
+        // in place: rows lane < i < ns of a[] hold -L[i][lane] and turn into X[i][lane]
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i > lane && i < ns) a[i] = -a[i];
+        for (int k = 1; k < ns; ++k) {
+            double xk = 0.0;
+            double c[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                c[i] = __shfl_sync(0xffffffffu, a[i], k);         // -L[i][k] for k < i < ns (untouched so far)
+                if (i == k) xk = a[i];                            // X[k][lane], final for lane < k
+            }
+            if (lane < k) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i > k && i < ns) a[i] += c[i] * xk;
+            }
+        }
+    }
+    // ---- write back through the tile (coalesced global stores)
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i >= lane) F[i + lane * FW_LD] = a[i];
+    __syncwarp();
+    for (int j = 0; j < ns; ++j) if (lane >= j && lane < nf) Lp[j * nf + lane] = F[lane + j * FW_LD];
+    if (nr > 0) {
+        double* Us = Ust + S.upd_off[s];
+        for (int j = ns; j < nf; ++j) if (lane >= j && lane < nf) Us[(lane - ns) + (int64_t)(j - ns) * nr] = F[lane + j * FW_LD];
+    }
+}
+
 // ------------------------------------------------------------------ G4b mid-size fronts (64 < nf <= 152)
 // Only the nf x ns panel lives in shared memory (a front of 128 x 30 needs 31 KB instead of
 // 128 KB => several CTAs per SM); the update block stays in global memory:
@@ -579,15 +689,27 @@ k_ldl_update_ldg(DevSym S, const int32_t* __restrict__ batch, int mode, int J0, 
     ldl_gemm_tile(Lp, ld, nf, D + f, u.ti * GBM, u.tj * GBM, u.k0, u.k1, acc, gsm);
     double* Us = Ust + S.upd_off[s];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double cv[4][4];
+    double* dc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const int col = u.tj * GBM + ty * 4 + c;
-        if (col < u.c_lo || col >= u.c_hi) continue;
-        double* dcol = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
+        const bool okc = col >= u.c_lo && col < u.c_hi;
+        dc[c] = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int row = u.ti * GBM + tx * 4 + a;
-            if (row < nf && row >= col) dcol[row] -= acc[a][c];
+            cv[a][c] = (okc && row < nf && row >= col) ? dc[c][row] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int col = u.tj * GBM + ty * 4 + c;
+        const bool okc = col >= u.c_lo && col < u.c_hi;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = u.ti * GBM + tx * 4 + a;
+            if (okc && row < nf && row >= col) dc[c][row] = cv[a][c] - acc[a][c];
         }
     }
 }
@@ -711,31 +833,54 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
     }
-    // ===== epilogue: subtract into the panel (col < ns) or the update block =====
+    // ===== epilogue: subtract into the panel (col < ns) or the update block.  All loads of a column
+    // pair are issued before the first store (a plain  *p -= v  loop serialises 64 load->store chains).
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+        double cv[2][8];
+        double* dc[2];
+        bool okc[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int col = u.tj * TB + wn + 8 * j + 2 * t + e;
-            if (col < u.c_lo || col >= u.c_hi) continue;
-            double* dcol = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
+            okc[e] = col >= u.c_lo && col < u.c_hi;
+            dc[e] = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = u.ti * TB + wm + 8 * i + g;
-                if (row < nf && row >= col) dcol[row] -= acc[i][j][e];
+                cv[e][i] = (okc[e] && row < nf && row >= col) ? dc[e][row] : 0.0;
             }
         }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = u.tj * TB + wn + 8 * j + 2 * t + e;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = u.ti * TB + wm + 8 * i + g;
+                if (okc[e] && row < nf && row >= col) dc[e][row] = cv[e][i] - acc[i][j][e];
+            }
+        }
+    }
 }
 
 // Pivot block J of the large fronts of a level: LDL' + inverse of the 64 x 64 diagonal block.
 // Parks [inv(L_JJ) strictly lower ; d on the diagonal] in the workspace.  One CTA per front.
+// 256 threads, thread (tx, ty) keeps the 4 x 4 tile (rows 4tx.., cols 4ty..) of the block AND of
+// X = inv(L) in registers.  One barrier per pivot: the owners of column k publish it (and the
+// owners of row k of X publish that row) in a double-buffered shared vector, then every thread
+// applies the rank-1 updates  A -= a_k a_k' / d_k  and  X -= l_k X[k,:]  to its own tiles
+// (inv(L) = (I - l_63 e_63') ... (I - l_0 e_0') applied to the identity, fused into the same sweep).
+// The sign-based dynamic regularisation (QDLDL: D[k]*sign < eps => D[k] = delta*sign) is evaluated
+// redundantly by every thread on the published pivot.
 __global__ void __launch_bounds__(256)
 k_piv_diag(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __restrict__ Lst,
            double* __restrict__ Wst, const int64_t* __restrict__ woff, double* __restrict__ D,
            double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
-    __shared__ double A[PB * (PB + 1)];               // column-major, ld = 65
+    __shared__ double colbuf[2][PB];            // column k of the (updated) block, unscaled
+    __shared__ double rowbuf[2][PB];            // row k of X
+    __shared__ double sgn[PB];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -743,136 +888,69 @@ k_piv_diag(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __
     const int ld = S.ld[s];
     const int nb = min(PB, ns - J0);
     const double* Lp = Lst + S.panel_off[s];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < PB * PB; e += 256) {
-        const int i = e & (PB - 1), j = e >> 6;
-        double v = 0.0;
-        if (i < nb && j < nb && i >= j) v = Lp[(int64_t)(J0 + j) * ld + J0 + i];
-        A[i + j * (PB + 1)] = v;
-    }
-    __syncthreads();
-    // ---- blocked LDL' of the 64 x 64 block in 4 panels of 16 columns.  Per panel: the 16 x 16
-    // diagonal sub-block is factored by warp 0 in registers (row per lane, shuffles broadcast the
-    // pivot column), the rows below are solved against it (thread per row) and the trailing part
-    // gets a rank-16 update from all threads: 3 barriers per panel instead of 2 per column.
-    __shared__ double Xs[48 * 17];
-    __shared__ double dvs[PB], dis[PB];
-    __shared__ double Sbuf[3 * 16 * 17];
-    const int lane = tid & 31, wid = tid >> 5;
-    constexpr int LDA = PB + 1;
-    for (int e = nb + tid; e < PB; e += 256) A[e + e * LDA] = 1.0;     // pad: identity beyond nb
-    __syncthreads();
-    for (int kb = 0; kb < PB; kb += 16) {
-        if (wid == 0) {
-            const int i = lane & 15;                   // lanes 16..31 mirror 0..15 (only < 16 write)
-            double a[16];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double a[4][4], x[4][4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = (j <= i) ? A[(kb + i) + (kb + j) * LDA] : 0.0;
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                double d = __shfl_sync(0xffffffffu, a[k], k);
-                const int gk = kb + k;
-                bool reg = false;
-                if (gk < nb) {
-                    const double sg = (double)S.dsign[f + J0 + gk];
-                    if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
-                }
-                const double dinv = 1.0 / d;
-                const double lik = a[k] * dinv;        // L[i][k] for i > k
-#pragma unroll
-                for (int j = k + 1; j < 16; ++j) {
-                    const double ajk = __shfl_sync(0xffffffffu, a[k], j);    // unscaled A[j][k]
-                    if (i >= j) a[j] -= lik * ajk;
-                }
-                if (i > k) a[k] = lik;
-                if (i == k) a[k] = d;
-                if (lane == 0) { dvs[gk] = d; dis[gk] = dinv; if (reg) atomicAdd(nreg, 1u); }
-            }
-            if (lane < 16) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (j <= i) A[(kb + i) + (kb + j) * LDA] = a[j];
-            }
+        for (int r = 0; r < 4; ++r) {
+            const int i = 4 * tx + r, j = 4 * ty + c;
+            double v = (i == j) ? 1.0 : 0.0;                     // identity beyond nb
+            if (i < nb && j < nb) v = (i >= j) ? Lp[(int64_t)(J0 + j) * ld + J0 + i] : 0.0;
+            a[r][c] = v;
+            x[r][c] = (i == j) ? 1.0 : 0.0;
         }
-        __syncthreads();
-        const int nbelow = PB - kb - 16;
-        if (tid < nbelow) {                            // x L11' = a ; L = x D^-1 ; X = x (= L D)
-            const int r = kb + 16 + tid;
-            double x[16];
+    if (tid < PB) sgn[tid] = tid < nb ? (double)S.dsign[f + J0 + tid] : 1.0;
+    unsigned int myreg = 0;
+#pragma unroll 1
+    for (int kq = 0; kq < PB / 4; ++kq) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = A[r + (kb + j) * LDA];
+        for (int kc = 0; kc < 4; ++kc) {
+            const int k = 4 * kq + kc;
+            double* cb = colbuf[k & 1];
+            double* rb = rowbuf[k & 1];
+            if (ty == kq) {
 #pragma unroll
-            for (int j = 1; j < 16; ++j) {
-                double v = x[j];
-#pragma unroll
-                for (int l = 0; l < 16; ++l) if (l < j) v -= x[l] * A[(kb + j) + (kb + l) * LDA];
-                x[j] = v;
+                for (int r = 0; r < 4; ++r) cb[4 * tx + r] = a[r][kc];
             }
+            if (tx == kq) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { Xs[tid * 17 + j] = x[j]; A[r + (kb + j) * LDA] = x[j] * dis[kb + j]; }
-        }
-        __syncthreads();
-        for (int e = tid; e < nbelow * nbelow; e += 256) {
-            const int ii = e % nbelow, jj = e / nbelow;
-            if (ii >= jj) {
-                double acc2 = 0.0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc2 += Xs[ii * 17 + k] * A[(kb + 16 + jj) + (kb + k) * LDA];
-                A[(kb + 16 + ii) + (kb + 16 + jj) * LDA] -= acc2;
-            }
-        }
-        __syncthreads();
-    }
-    for (int k = tid; k < nb; k += 256) { D[f + J0 + k] = dvs[k]; Dinv[f + J0 + k] = dis[k]; }
-    // ---- blocked inverse X = inv(L) of the unit-lower factor (16 x 16 blocks).  X[r][c] (r > c) is
-    // written into the unused upper triangle at A[c + r*LDA].
-    auto Xat = [&](int r, int c) -> double { return r > c ? A[c + r * LDA] : (r == c ? 1.0 : 0.0); };
-    if (tid < PB) {                                    // diagonal blocks: thread = (block I, column j)
-        const int I = tid >> 4, j = tid & 15, o = I * 16;
-        double x[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 1; i < 16; ++i) {
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) if (k >= j && k < i) v -= A[(o + i) + (o + k) * LDA] * x[k];
-            if (i > j) x[i] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if (i > j) A[(o + j) + (o + i) * LDA] = x[i];
-    }
-    __syncthreads();
-    {
-        const int i = tid >> 4, j = tid & 15;          // element of a 16 x 16 block
-        for (int dist = 1; dist < 4; ++dist) {
-            for (int J = 0; J + dist < 4; ++J) {       // S = sum_K L_IK X_KJ
-                const int I = J + dist;
-                double sacc = 0.0;
-                for (int K = J; K < I; ++K)
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-                        sacc += A[(I * 16 + i) + (K * 16 + k) * LDA] * Xat(K * 16 + k, J * 16 + j);
-                Sbuf[J * 16 * 17 + i * 17 + j] = sacc;
+                for (int c = 0; c < 4; ++c) rb[4 * ty + c] = x[kc][c];
             }
             __syncthreads();
-            for (int J = 0; J + dist < 4; ++J) {       // X_IJ = -X_II S
-                const int I = J + dist;
-                double xacc = 0.0;
+            double d = cb[k];
+            const double sg = sgn[k];
+            bool reg = false;
+            if (k < nb && rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
+            const double dinv = 1.0 / d;
+            if (tid == 0) { if (k < nb) { D[f + J0 + k] = d; Dinv[f + J0 + k] = dinv; } if (reg) ++myreg; }
+            double li[4], cj[4], xr[4];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) if (k <= i) xacc += Xat(I * 16 + i, I * 16 + k) * Sbuf[J * 16 * 17 + k * 17 + j];
-                A[(J * 16 + j) + (I * 16 + i) * LDA] = -xacc;
+            for (int r = 0; r < 4; ++r) { const int i = 4 * tx + r; li[r] = (i > k) ? cb[i] * dinv : 0.0; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const int j = 4 * ty + c; cj[c] = (j > k) ? cb[j] : 0.0; xr[c] = rb[j]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { a[r][c] -= li[r] * cj[c]; x[r][c] -= li[r] * xr[c]; }
+            if (ty == kq) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { const int i = 4 * tx + r; if (i > k) a[r][kc] = li[r]; else if (i == k) a[r][kc] = d; }
             }
-            __syncthreads();
         }
     }
+    if (tid == 0 && myreg) atomicAdd(nreg, myreg);
     // park [inv(L_JJ) strictly lower ; d on the diagonal] (column-major 64 x 64)
     double* Wd = Wst + woff[blockIdx.x] + (int64_t)(J0 / PB) * (PB * PB);
-    for (int e = tid; e < PB * PB; e += 256) {
-        const int i = e % PB, j = e / PB;
-        double v = (i == j) ? 1.0 : 0.0;
-        if (i < nb && j < nb) { if (i > j) v = A[j + i * (PB + 1)]; else if (i == j) v = A[i + j * (PB + 1)]; }
-        Wd[e] = v;
-    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = 4 * tx + r, j = 4 * ty + c;
+            double v = (i == j) ? 1.0 : 0.0;
+            if (i < nb && j < nb) { if (i > j) v = x[r][c]; else if (i == j) v = a[r][c]; }
+            Wd[i + j * PB] = v;
+        }
 }
 
 // L[rows, J] = F[rows, J] * inv(L_JJ)' * D_J^-1 for a 64-row tile below the pivot block.
@@ -1122,9 +1200,28 @@ k_bwd_leaf(DevSym S, const int32_t* __restrict__ batch, int count, const double*
     y[f] = acc;
 }
 
-// --- narrow supernodes (ns <= 32): one warp per supernode, WPB warps per CTA
+// --- narrow supernodes (ns <= 32, nf <= 192): one warp per supernode, WPB warps per CTA.
+// Every L entry is used exactly once per sweep, so what matters is memory-level parallelism: each
+// phase issues ALL its loads (up to 32 per lane, one per pivot column, coalesced across lanes)
+// before the first use; a supernode costs ~4 dependent memory latencies instead of ~ns.
 constexpr int WPB = 8;
-__global__ void __launch_bounds__(WPB * 32)
+
+// lane l <- sum over lanes of p[l]  (32 accumulators per lane, 31 shuffles, fixed order => deterministic)
+__device__ __forceinline__ double warp_transpose_reduce(double (&p)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int idx = 0; idx < off; ++idx) {
+            const double send = hi ? p[idx] : p[idx + off];
+            const double keep = hi ? p[idx + off] : p[idx];
+            p[idx] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return p[0];
+}
+
+__global__ void __launch_bounds__(WPB * 32, 2)
 k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
            const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
     extern __shared__ double smem[];
@@ -1139,6 +1236,11 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
     const int ld = S.ld[s];
+    const double* Lp = Lst + S.panel_off[s];
+    // the triangle loads do not depend on the gathered right-hand side: issue them first
+    double v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
     {
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
         const int64_t base = S.asm_base[s];
@@ -1149,23 +1251,25 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
         }
     }
     __syncwarp();
-    const double* Lp = Lst + S.panel_off[s];
-    double xi = 0.0;
-    if (lane < ns) {
-        xi = w[lane];
-        for (int j = 0; j < lane; ++j) xi += Lp[(int64_t)j * ld + lane] * w[j];
-    }
+    // x = inv(L11) w_top : x_i = w_i + sum_{j<i} X[i][j] w_j
+    double xi = (lane < ns) ? w[lane] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < ns) xi += v[j] * w[j];
     __syncwarp();
     if (lane < ns) { w[lane] = xi; y[f + lane] = xi; }
     __syncwarp();
+    // u = w_bot - L21 x : one row per lane, all ns column loads of a row in flight together
     for (int r = ns + lane; r < nf; r += 32) {
-        double acc = w[r];
-        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * ld + r] * w[j];
-        uvec[rp + r - ns] = acc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
+        uvec[rp + r - ns] = w[r] - (a0 + a1);
     }
 }
 
-__global__ void __launch_bounds__(WPB * 32)
+__global__ void __launch_bounds__(WPB * 32, 2)
 k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
            const double* __restrict__ Lst, const double* __restrict__ Dinv, double* __restrict__ y) {
     extern __shared__ double smem[];
@@ -1180,25 +1284,32 @@ k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     const int nr = (int)(S.rows_ptr[s + 1] - rp);
     const int nf = ns + nr;
     const int ld = S.ld[s];
+    const double* Lp = Lst + S.panel_off[s];
     for (int i = lane; i < nf; i += 32) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
     __syncwarp();
-    const double* Lp = Lst + S.panel_off[s];
-    // t_j = w_j - sum_r L[r,j] w_r  (lane j keeps t_j)
-    double tj = 0.0;
-    for (int j = 0; j < ns; ++j) {
-        const double* cj = Lp + (int64_t)j * ld;
-        double acc = 0.0;
-        for (int r = ns + lane; r < nf; r += 32) acc += cj[r] * w[r];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == j) tj = w[j] - acc;
+    // t_j = w_j - sum_{r >= ns} L[r][j] w_r : lane owns rows r, keeps one partial sum per column j
+    double p[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) p[j] = 0.0;
+    for (int r = ns + lane; r < nf; r += 32) {
+        double v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
+        const double wr = w[r];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p[j] += v[j] * wr;
     }
-    // x_j = t_j + sum_{i>j} Linv[i,j] t_i
-    double xj = tj;
-    for (int i = 1; i < ns; ++i) {
-        const double ti = __shfl_sync(0xffffffffu, tj, i);
-        if (lane < i && lane < ns) xj += Lp[(int64_t)lane * ld + i] * ti;
-    }
-    if (lane < ns) y[f + lane] = xj;
+    // the triangle (row `lane`): X[lane][j], j < lane - issued before the reduction shuffles
+    double xr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xr[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    const double red = warp_transpose_reduce(p, lane);
+    const double tj = (lane < ns) ? w[lane] - red : 0.0;
+    // x_j = t_j + sum_{i>j} X[i][j] t_i : lane i contributes X[i][j] t_i to column j
+#pragma unroll
+    for (int j = 0; j < 32; ++j) p[j] = xr[j] * tj;
+    const double corr = warp_transpose_reduce(p, lane);
+    if (lane < ns) y[f + lane] = tj + corr;
 }
 
 // --- tiny supernodes (ns <= 8, nf <= 32, with children): 8 lanes per supernode, 32 supernodes
@@ -1398,9 +1509,12 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
 constexpr int WP = 256;        // panel width
 constexpr int BRT = 64;        // rows per CTA in the GEMV kernels
 
-// w = [y_s ; 0] + sum of children contributions (destination-owner form); grid (row tiles, cnt)
-// AL lanes cooperate on one destination row (AL = 32 for fronts with thousands of children);
-// the cross-lane sum is a fixed-order shuffle tree, so the result is deterministic.
+// w = [y_s ; 0] + sum of children contributions (destination-owner form).
+// AL lanes cooperate on one destination row: AL = 1 (thread per row), 32 (warp per row: fronts with
+// many children) or 256 (CTA per row: root fronts with ~1e5 children, ~1e3 sources per row).  The
+// index loads of 8 sources are issued together, then their 8 value loads (two dependent latencies
+// per 8 sources instead of 16); the cross-lane sum is a fixed-order tree => deterministic.
+// grid: AL < 256: (ceil(maxnf * AL / 256), cnt) ; AL = 256: (maxnf, cnt).
 template <int AL>
 __global__ void __launch_bounds__(256)
 k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ y,
@@ -1410,19 +1524,47 @@ k_big_asm_fwd(DevSym S, const int32_t* __restrict__ batch, double* __restrict__ 
     const int ns = S.sn_first[s + 1] - f;
     const int64_t rp = S.rows_ptr[s];
     const int nf = ns + (int)(S.rows_ptr[s + 1] - rp);
-    const int i = (blockIdx.x * 256 + threadIdx.x) / AL;
+    const int i = (AL == 256) ? (int)blockIdx.x : (int)((blockIdx.x * 256 + threadIdx.x) / AL);
     const int sub = threadIdx.x % AL;
     double acc = 0.0;
     if (i < nf) {
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
         const int64_t base = S.asm_base[s];
-        for (int e = cp[i] + sub; e < cp[i + 1]; e += AL)
+        const int e1 = cp[i + 1];
+        int e = cp[i] + sub;
+        for (; e + 7 * AL < e1; e += 8 * AL) {
+            int32_t q[8]; bool on[8]; double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                q[u] = S.asm_src[base + e + u * AL];
+                on[u] = !S.active || S.active[S.asm_child[base + e + u * AL]];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = on[u] ? uvec[q[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; e < e1; e += AL)
             if (!S.active || S.active[S.asm_child[base + e]]) acc += uvec[S.asm_src[base + e]];
     }
+    if (AL == 256) {
+        __shared__ double red[8];
 #pragma unroll
-    for (int o = AL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (i < nf && sub == 0) {
-        if (i < ns) y[f + i] += acc; else uvec[rp + i - ns] = acc;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0 && i < nf) {
+            double t = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
+            if (i < ns) y[f + i] += t; else uvec[rp + i - ns] = t;
+        }
+    } else {
+#pragma unroll
+        for (int o = AL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (i < nf && sub == 0) {
+            if (i < ns) y[f + i] += acc; else uvec[rp + i - ns] = acc;
+        }
     }
 }
 

@@ -728,6 +728,140 @@ bool nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, d
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// Ordering for KKT systems with dense cone blocks (PSD cones: cliques of n(n+1)/2 rows).
+//   phase 1: every vertex outside the blocks (the primal variables, the rows of diagonal cones) in
+//            the AMD-class order of their induced subgraph.  Late in the IP iteration a PSD block
+//            Hs = (RR') (x)s (RR') has a dynamic range > 1e10; eliminating the variables it is
+//            coupled to FIRST turns the block into the (negative definite, far better conditioned)
+//            Schur complement -Hs - A P^-1 A' before any of its pivots is taken - that is what the
+//            reference's AMD order does implicitly and what keeps the pivots' signs.
+//   phase 2: the blocks themselves in a nested-dissection order of the block quotient graph (two
+//            blocks are adjacent if a connected piece of the phase-1 vertices touches both), whole
+//            blocks as separators, natural order inside a block.  The elimination of a definite
+//            matrix is stable in any order, so phase 2 is free to trade flops for tree shape: a
+//            chain of k coupled cones becomes a tree of depth log2 k whose fronts batch per level,
+//            instead of a k-level chain of single large fronts (C4: 1463 levels -> 21).
+// Returns false (perm_out untouched) when the structure does not fit: fewer than `min_blocks`
+// blocks, or a phase-1 component that touches too many blocks (the quotient graph would be dense).
+bool order_blocks_last_nd(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                          const int32_t* block_id, int32_t min_blocks, int32_t* perm_out) {
+    if (!block_id || n == 0) return false;
+    int32_t nb = 0;
+    for (int32_t i = 0; i < n; ++i) nb = std::max(nb, block_id[i] + 1);
+    if (nb < min_blocks) return false;
+    std::vector<std::vector<int32_t>> members(nb);
+    std::vector<int32_t> loc(n, -1), free_v;
+    for (int32_t i = 0; i < n; ++i) {
+        if (block_id[i] >= 0) members[block_id[i]].push_back(i);
+        else { loc[i] = (int32_t)free_v.size(); free_v.push_back(i); }
+    }
+    const int32_t k = (int32_t)free_v.size();
+    // ---- phase 1: AMD-class order of the induced subgraph of the free vertices
+    std::vector<int32_t> order1(k);
+    {
+        std::vector<int64_t> lx(k + 1, 0); std::vector<int32_t> la;
+        for (int32_t i = 0; i < k; ++i) {
+            const int32_t v = free_v[i];
+            for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) if (loc[adj[p]] >= 0) la.push_back(loc[adj[p]]);
+            lx[i + 1] = (int64_t)la.size();
+        }
+        if (k > 0) amd_order_graph(k, lx.data(), la.data(), dense_scale, order1.data());
+    }
+    // ---- block quotient graph through the connected pieces of the free vertices
+    std::vector<std::vector<int32_t>> H(nb);
+    {
+        std::vector<int32_t> comp(k, -1), stack, touched;
+        std::vector<int32_t> mark(nb, -1);
+        int32_t nc = 0;
+        for (int32_t r = 0; r < k; ++r) {
+            if (comp[r] >= 0) continue;
+            touched.clear(); stack.assign(1, r); comp[r] = nc;
+            while (!stack.empty()) {
+                const int32_t u = stack.back(); stack.pop_back();
+                const int32_t v = free_v[u];
+                for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                    const int32_t w = adj[p];
+                    if (loc[w] >= 0) { if (comp[loc[w]] < 0) { comp[loc[w]] = nc; stack.push_back(loc[w]); } }
+                    else { const int32_t b = block_id[w]; if (mark[b] != nc) { mark[b] = nc; touched.push_back(b); } }
+                }
+            }
+            if (touched.size() > 64) return false;
+            for (size_t a = 0; a < touched.size(); ++a)
+                for (size_t c = a + 1; c < touched.size(); ++c) { H[touched[a]].push_back(touched[c]); H[touched[c]].push_back(touched[a]); }
+            ++nc;
+        }
+        for (int32_t b = 0; b < nb; ++b)                      // direct block-block entries
+            for (int32_t v : members[b])
+                for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                    const int32_t b2 = block_id[adj[p]];
+                    if (b2 >= 0 && b2 != b) H[b].push_back(b2);
+                }
+        for (auto& l : H) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
+    }
+    // ---- phase 2: nested dissection of the quotient graph (weights = block sizes)
+    std::vector<int32_t> border; border.reserve(nb);
+    std::vector<int32_t> piece(nb, 0), lev(nb, -1);
+    int32_t next_piece = 1;
+    struct Rec {
+        std::vector<std::vector<int32_t>>& H; std::vector<std::vector<int32_t>>& members;
+        std::vector<int32_t>& piece; std::vector<int32_t>& lev; int32_t& next_piece; std::vector<int32_t>& out;
+        void bfs(int32_t root, int32_t lab, std::vector<int32_t>& q) {
+            q.assign(1, root); lev[root] = 0;
+            for (size_t h = 0; h < q.size(); ++h)
+                for (int32_t u : H[q[h]]) if (piece[u] == lab && lev[u] < 0) { lev[u] = lev[q[h]] + 1; q.push_back(u); }
+        }
+        void run(std::vector<int32_t> verts) {
+            if (verts.empty()) return;
+            if (verts.size() <= 2) { for (int32_t v : verts) { out.push_back(v); piece[v] = -1; } return; }
+            const int32_t lab = piece[verts[0]];
+            std::vector<int32_t> q;
+            for (int32_t v : verts) lev[v] = -1;
+            bfs(verts[0], lab, q);
+            if (q.size() < verts.size()) {                    // disconnected: every component on its own
+                std::vector<std::vector<int32_t>> comps; comps.push_back(q);
+                for (int32_t v : verts) if (lev[v] < 0) { bfs(v, lab, q); comps.push_back(q); }
+                for (auto& c : comps) { const int32_t nl = next_piece++; for (int32_t v : c) piece[v] = nl; }
+                for (auto& c : comps) run(c);
+                return;
+            }
+            int32_t root = q.back();                          // pseudo-peripheral: two more sweeps
+            for (int it = 0; it < 2; ++it) { for (int32_t v : verts) lev[v] = -1; bfs(root, lab, q); root = q.back(); }
+            for (int32_t v : verts) lev[v] = -1;
+            bfs(root, lab, q);
+            const int32_t nlev = lev[q.back()] + 1;
+            if (nlev < 3) { for (int32_t v : q) { out.push_back(v); piece[v] = -1; } return; }
+            std::vector<int64_t> lw(nlev, 0); int64_t tot = 0;
+            for (int32_t v : q) { lw[lev[v]] += (int64_t)members[v].size(); tot += (int64_t)members[v].size(); }
+            int32_t best = -1; double bs = 1e300; int64_t cum = 0;
+            for (int32_t l = 0; l < nlev; ++l) {
+                const int64_t before = cum; cum += lw[l];
+                if (l == 0 || l == nlev - 1) continue;
+                const double bal = (double)std::min(before, tot - cum) / (double)tot;
+                const double score = (double)lw[l] / (0.05 + bal);
+                if (score < bs) { bs = score; best = l; }
+            }
+            std::vector<int32_t> A, B, Sp;
+            for (int32_t v : q) (lev[v] < best ? A : (lev[v] > best ? B : Sp)).push_back(v);
+            const int32_t la = next_piece++, lb = next_piece++;
+            for (int32_t v : A) piece[v] = la;
+            for (int32_t v : B) piece[v] = lb;
+            for (int32_t v : Sp) piece[v] = -2;
+            run(A); run(B);
+            for (int32_t v : Sp) { out.push_back(v); piece[v] = -1; }
+        }
+    } rec{H, members, piece, lev, next_piece, border};
+    {
+        std::vector<int32_t> all(nb); std::iota(all.begin(), all.end(), 0);
+        rec.run(all);
+    }
+    if ((int32_t)border.size() != nb) return false;
+    int32_t pos = 0;
+    for (int32_t i = 0; i < k; ++i) perm_out[pos++] = free_v[order1[i]];
+    for (int32_t b : border) for (int32_t v : members[b]) perm_out[pos++] = v;
+    return pos == n;
+}
+
 }  // namespace cb200
 
 extern "C" int32_t cb200_order_amd(int64_t n, const int64_t* colptr, const int64_t* rowval,

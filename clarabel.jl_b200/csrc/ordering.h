@@ -15,6 +15,10 @@ void nd_order_graph(int32_t n, const int64_t* xadj, const int32_t* adj, double d
 bool nd_order_graph_blocks(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
                            int32_t leaf_size, const int32_t* block_id, int32_t* perm_out,
                            bool skip_unsplit = false);
+// PSD-aware ordering (see ordering.cpp): vertices outside the dense cone blocks first (AMD-class),
+// then the blocks in a nested-dissection order of the block quotient graph.  false = not applicable.
+bool order_blocks_last_nd(int32_t n, const int64_t* xadj, const int32_t* adj, double dense_scale,
+                          const int32_t* block_id, int32_t min_blocks, int32_t* perm_out);
 }  // namespace cb200
 
 extern "C" {

@@ -117,8 +117,19 @@ void symbolic_analyze(int64_t N64, const int64_t* colptr, const int64_t* rowval,
         S.ordering_used = 0;
         std::vector<int64_t> xadj; std::vector<int32_t> adj;
         build_sym_graph(N, colptr, rowval, xadj, adj);
+        bool has_blocks = false;
+        if (opt.block_id) for (int32_t i = 0; i < N && !has_blocks; ++i) has_blocks = opt.block_id[i] >= 0;
         if (opt.ordering != 1) {
             amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
+        } else if (has_blocks) {
+            // dense cone blocks (PSD): their coupled variables first, then the blocks by nested
+            // dissection of the block graph; the AMD-class order when that structure does not fit.
+            // The generic vertex dissection below is never used here (it may eliminate a block before
+            // the variables it is coupled to: wrong-sign pivots late in the iteration).
+            if (order_blocks_last_nd(N, xadj.data(), adj.data(), opt.dense_scale, opt.block_id, opt.min_cone_blocks, p0.data()))
+                S.ordering_used = 4;
+            else
+                amd_order_graph(N, xadj.data(), adj.data(), opt.dense_scale, p0.data());
         } else {
             // auto: nested dissection (shallow, wide trees for the level-scheduled kernels and the
             // multi-GPU split) unless it costs more than nd_max_cost_ratio x the AMD-class ordering.

@@ -22,7 +22,9 @@ struct SymbolicOptions {
     int32_t collapse_nf = 32;    // a whole subtree whose merged front (all its columns + the rows below its
                                  // root) has at most this many rows becomes ONE dense supernode (0 = off)
     const int32_t* block_id = nullptr;   // optional [N]: rows sharing an id >= 0 form a dense cone block
-                                         // (clique) that nested dissection must not cut
+                                         // (clique): ordering 1 then eliminates everything else first and
+                                         // dissects the block graph (order_blocks_last_nd)
+    int32_t min_cone_blocks = 8;         // fewer blocks than this: AMD-class order
     // Size classes of the numeric factorisation (the large-front path pads its panels, so the
     // symbolic layout has to know which fronts take it): panel-in-smem kernel for
     // panel_min_nf < nf <= panel_max_nf (if it fits), shared-memory front kernel up to small_max_nf,
@@ -80,7 +82,8 @@ struct Symbolic {
     double flops = 0;               // sum over pivot columns of (col length incl. diag)^2
     int64_t upd_total = 0;          // doubles in update storage
     int32_t max_front = 0, max_width = 0;
-    int32_t ordering_used = 0;      // 0 = AMD-class, 1 = nested dissection, 2 = natural, 3 = caller's permutation
+    int32_t ordering_used = 0;      // 0 = AMD-class, 1 = nested dissection, 2 = natural, 3 = caller's permutation,
+                                    // 4 = cone-block dissection (variables first, PSD blocks by ND of the block graph)
     inline int32_t ns(int32_t s) const { return sn_first[s + 1] - sn_first[s]; }
     inline int32_t nr(int32_t s) const { return (int32_t)(rows_ptr[s + 1] - rows_ptr[s]); }
 };

@@ -113,10 +113,10 @@ class B200DirectLDLSolver:
         return {self._L.cb200_fine_timer_name(i).decode(): float(out[i]) for i in range(n)}
 
     def stats(self):
-        out = np.zeros(12)
-        self._L.cb200_get_stats(self._h, _p(out), 12)
+        out = np.zeros(14)
+        self._L.cb200_get_stats(self._h, _p(out), 14)
         keys = ["flops", "schur_flops", "panel_flops", "nnzL", "nlevels", "nsuper", "nlarge",
-                "big_solve_bytes", "upd_bytes", "panel_bytes", "ordering_used", "rank_flops"]
+                "big_solve_bytes", "upd_bytes", "panel_bytes", "ordering_used", "rank_flops", "use_tma", "tma_kmajor"]
         return dict(zip(keys, out.tolist()))
 
     def reset_timers(self):
@@ -174,17 +174,10 @@ class B200KKTSolver:
         self.KKT, self.map = assemble_kkt_matrix(P, A, cones)
         self.p = cones.p
         self.Dsigns = fill_Dsigns(m, n, self.p, cones)
-        # Ordering choice.  Nested dissection gives the shallow, wide trees the level-scheduled
-        # kernels want, but its separators can cut through the dense clique of a PSD cone block;
-        # late in the IP iteration those blocks have a dynamic range > 1e10 and a split clique was
-        # observed to produce wrong-sign pivots (dynamic regularisation firing, growth, NaN) where
-        # the reference's AMD order does not.  Problems with dense PSD blocks therefore keep the
-        # reference's AMD-class ordering (their fronts are large: parallelism comes from inside
-        # the fronts, not from the tree).
-        if "ordering" not in cs_over:
-            from .cones import PSD
-            has_psd = bool(((cones.types == PSD) & (cones.dims > 2)).any())
-            cs_over = dict(cs_over, ordering=0 if has_psd else 1)
+        # Ordering: left to the library (cb200_settings.ordering = 1, auto).  It detects dense PSD cone
+        # blocks from the pattern + Dsigns and then eliminates the variables coupled to them first and
+        # dissects the block graph (or falls back to the AMD-class order for a handful of blocks); see
+        # cb200_create in csrc/api_cuda.cu and DESIGN.md section 5.  The Julia shim gets the same rule.
         if "device" not in cs_over:
             cs_over = dict(cs_over, device=int(os.environ.get("LOCAL_RANK", "0")))
         self.ldl = B200DirectLDLSolver(self.KKT, self.Dsigns, settings, **cs_over)

@@ -43,7 +43,8 @@ typedef struct cb200_settings {
     double  iterative_refinement_abstol;          /* :129  (1e-12) */
     int32_t iterative_refinement_max_iter;        /* :131  (10) */
     double  iterative_refinement_stop_ratio;      /* :132  (5) */
-    int32_t ordering;                   /* 0 AMD, 1 auto: nested dissection unless > 3x AMD cost (default), 2 natural */
+    int32_t ordering;                   /* 0 AMD, 1 auto (default): nested dissection unless > 3x AMD cost;
+                                         * AMD when K holds a dense PSD cone block (detected from pattern + Dsigns), 2 natural */
     double  amd_dense_scale;            /* dense-row threshold multiplier (reference QDLDL path: 1.5, directldl_qdldl.jl:24; default here 0.3) */
     int32_t nd_leaf_size;
     int32_t use_cuda_graph;             /* bit mask: 1 replay the solve sweeps, 2 the factorisation, through CUDA graphs */

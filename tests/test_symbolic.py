@@ -172,3 +172,78 @@ def test_symbolic_maps_on_random_quasidefinite_patterns(seed):
         assert np.all(np.sign(D) == Ds[a["perm"]]) and mf.nreg == 0
         x = mf.solve(b)
         assert np.abs(x - xs).max() < 1e-8 * max(1.0, np.abs(xs).max())
+
+
+def _sdp_chain(cb, ncones=12, side=10):
+    return cb.problems.c4_sdp(ncones=ncones, side=side, n=40 * ncones, vars_per_cone=70)
+
+
+def test_cone_block_dissection_order(cb):
+    """Ordering 1 with dense cone blocks (PSD): every vertex outside the blocks comes before the
+    blocks, the blocks are dissected (shallow tree instead of a chain), and the maps of that
+    ordering factor / solve correctly (numpy multifrontal vs SuperLU)."""
+    from clarabel_jl_b200 import lib
+    from clarabel_jl_b200 import kkt_assembly as ka
+    P, q, A, b, K = _sdp_chain(cb)
+    data = cb.problemdata.ProblemData(P, q, A, b, K, cb.Settings())
+    cones = cb.CompositeCone(data.cones)
+    KKT, mp = ka.assemble_kkt_matrix(data.P, data.A, cones)
+    N = KKT.shape[0]
+    bid = lib.cone_block_ids(cones, data.n, N)
+    assert bid is not None and bid.max() == 11
+    Sa = lib.Symbolic(KKT, ordering=0)
+    Sn = lib.Symbolic(KKT, ordering=1, block_id=bid)
+    a = Sn.arrays()
+    perm = a["perm"]
+    assert sorted(perm.tolist()) == list(range(N))
+    # every vertex outside the blocks is eliminated before each block row it is coupled to (the final
+    # permutation is the postorder of the elimination tree, so "variables first" holds along every
+    # root path, not as one global prefix)
+    pos = np.empty(N, dtype=np.int64); pos[perm] = np.arange(N)
+    Kc = sym_full(KKT).tocoo()
+    sel = (bid[Kc.row] >= 0) & (bid[Kc.col] < 0)
+    assert np.all(pos[Kc.col[sel]] < pos[Kc.row[sel]])
+    assert Sn.stats["nlevels"] < Sa.stats["nlevels"]           # the chain of cones became a tree
+    Ds = ka.fill_Dsigns(data.m, data.n, cones.p, cones)
+    rng = np.random.default_rng(0)
+    Kv = KKT.copy()
+    Kv.data[mp.diag_full] += np.where(Ds > 0, 1.0 + rng.random(N), -1.0 - rng.random(N))
+    diag_set = set(mp.diag_full.tolist())
+    off = np.array([k for k in mp.Hsblocks if k not in diag_set], dtype=np.int64)
+    Kv.data[off] = 0.01 * rng.standard_normal(len(off))
+    mf = MFNumpy(a)
+    D = mf.factor(Kv.data, Ds)
+    assert np.all(np.sign(D) == Ds[perm])
+    bb = rng.standard_normal(N)
+    x = mf.solve(bb)
+    Kf = sym_full(Kv)
+    assert np.abs(Kf @ x - bb).max() < 1e-9 * max(1.0, np.abs(x).max())
+
+
+def test_cone_block_dissection_is_numerically_equivalent_to_amd(cb):
+    """The whole IP solve through the QDLDL oracle with the cone-block dissection order: same
+    status, same iteration count, no dynamically regularised pivot - like the AMD-class order
+    (late iterates of an SDP are where a wrong elimination order of the PSD blocks shows)."""
+    from clarabel_jl_b200 import lib
+    from oracle.kktsolver_oracle import OracleDirectLDLKKTSolver
+    P, q, A, b, K = _sdp_chain(cb, ncones=10, side=8)
+    sols = {}
+    for name in ("amd", "cone_nd"):
+        class O(OracleDirectLDLKKTSolver):
+            def __init__(self, P_, A_, cones, m, n, settings, _name=name):
+                perm = None
+                if _name == "cone_nd":
+                    from clarabel_jl_b200 import kkt_assembly as ka
+                    KKT, _ = ka.assemble_kkt_matrix(P_, A_, cones)
+                    S = lib.Symbolic(KKT, ordering=1, block_id=lib.cone_block_ids(cones, n, KKT.shape[0]))
+                    assert S.stats["N"] == KKT.shape[0]
+                    perm = S.arrays()["perm"]
+                super().__init__(P_, A_, cones, m, n, settings, perm=perm)
+        cb.register_kktsolver("qd_" + name, O)
+        s = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="qd_" + name))
+        sol = s.solve()
+        sols[name] = (sol, s.kktsystem.kktsolver.ldl.regularize_count)
+    (sa, ra), (sn, rn) = sols["amd"], sols["cone_nd"]
+    assert sa.status_name == sn.status_name == "SOLVED"
+    assert sa.iterations == sn.iterations and ra == rn == 0
+    assert abs(sa.obj_val - sn.obj_val) <= 1e-8 * max(1.0, abs(sa.obj_val))

@@ -18,12 +18,11 @@ from clarabel_jl_b200 import problems  # noqa: E402
 
 
 def run(name, nsteps=3):
-    gen, kw, _, _ = bench.WORKLOADS[name]
-    P, q, A, b, K = getattr(problems, gen)(**kw)
+    P, q, A, b, K = bench.make_problem(name)
     solver = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200"))
     ks = solver.kktsystem.kktsolver
-    rec = bench.Recorder(ks, solver.cones)
-    solver.solve(max_iter=bench.REPLAY_ITERS)
+    rec = bench.Recorder(ks)
+    solver.solve(max_iter=int(os.environ.get("CB200_FINE_ITERS", "3")))
     rec.detach()
     replay = [s for s in rec.steps[1:] if len(s["rhs"]) == 3] or rec.steps[-1:]
     lx, lz = np.zeros(solver.data.n), np.zeros(solver.data.m)
@@ -45,6 +44,7 @@ def run(name, nsteps=3):
     per = {k: v / nsteps for k, v in fine.items() if v > 0}
     tot = sum(per.values())
     st = ks.ldl.stats()
+    print(f"   [stats] tma={int(st.get('use_tma', -1))} kmajor={int(st.get('tma_kmajor', -1))} ordering={int(st.get('ordering_used', -1))}")
     print(f"== {name}: N={ks.KKT.shape[0]} nnzL={int(st['nnzL'])} levels={int(st['nlevels'])} supernodes={int(st['nsuper'])} "
           f"| per step: factor {tm['factor_ms'] / nsteps:.2f} ms, solves {tm['solve_ms'] / nsteps:.2f} ms "
           f"({tm['nsolve'] / nsteps:.1f} sweeps), spmv {tm['spmv_ms'] / nsteps:.2f} ms, launches {tm['nlaunch'] / nsteps:.0f}")
