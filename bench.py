@@ -56,7 +56,7 @@ WORKLOADS = {
     "C4r": ("c4_sdp", {"ncones": 40, "side": 40, "n": 8000, "vars_per_cone": 300}),
     "C5": ("c5_block_angular", {}),
 }
-ORDERING_NAMES = {0: "amd", 1: "nested-dissection", 2: "natural", 3: "user"}
+ORDERING_NAMES = {0: "amd", 1: "nested-dissection", 2: "natural", 3: "user", 4: "cone-block-dissection"}
 CPU_LEG_LIMIT_S = float(os.environ.get("CB200_CPU_LEG_LIMIT", "330"))      # wall clock, b200 arm
 REF_ARM_BUDGET_S = float(os.environ.get("CB200_REF_BUDGET", "200"))        # timed CPU work, reference arm
 

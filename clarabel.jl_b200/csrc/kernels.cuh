@@ -558,6 +558,15 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// The wide FP64 tensor-core shape (sm_90+): D(16x8) += A(16x16) B(16x8).  Fragment layout (lane = 4 g + t):
+//   a[2 v + h] = A[g + 8 h][t + 4 v]   b[v] = B[t + 4 v][g]   c[2 h + e] = C[g + 8 h][2 t + e]
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+                 "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                   "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
 
 // Tile decode shared by both GEMM versions.  Updated elements: c_lo <= col < c_hi, col <= row < nf
 // with k in [k0, k1).  Tiles of size T are anchored at front-local index 0.
@@ -798,37 +807,41 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
         }
         return;
     }
-    // ===== 8 consumer warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA fragments =====
+    // ===== 8 consumer warps (2 x 4), warp tile 64 x 32 = 4 x 4 DMMA m16n8k16 tiles per k-slab =====
     const int sk = kmajor ? 8 : TB, srg = kmajor ? TK * 8 : 8;      // strides (doubles) of k and of a row-group
     const int wm = (wid & 1) * 64, wn = (wid >> 1) * 32;
     const int g = lane >> 2, t = lane & 3;
     const double* Dv = D + f;
-    double acc[8][4][2];
+    double acc[4][4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
     for (int it = 0; it < nk; ++it) {
         const int st = it % TSTAGES;
         const uint32_t ph = (uint32_t)(it / TSTAGES) & 1u;
         double dv[4];
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) { const int k = u.k0 + it * TK + k4 * 4 + t; dv[k4] = (k < u.k1) ? Dv[k] : 0.0; }
+        for (int v = 0; v < 4; ++v) { const int k = u.k0 + it * TK + 4 * v + t; dv[v] = (k < u.k1) ? Dv[k] : 0.0; }
         mbar_wait(full + st, ph);
         const double* A = sA + st * TTILE + (wm / 8) * srg + g;
         const double* B = sB + st * TTILE + (wn / 8) * srg + g;
+        double bf[4][4];
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-            const int ko = (k4 * 4 + t) * sk;
-            double af[8], bf[4];
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = A[i * srg + ko];
+            for (int v = 0; v < 4; ++v) bf[j][v] = B[j * srg + (4 * v + t) * sk] * dv[v];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = B[j * srg + ko] * dv[k4];
+        for (int i = 0; i < 4; ++i) {
+            double af[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int v = 0; v < 4; ++v)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int h = 0; h < 2; ++h) af[2 * v + h] = A[(2 * i + h) * srg + (4 * v + t) * sk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma16816(acc[i][j], af, bf[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
@@ -859,7 +872,8 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = u.ti * TB + wm + 8 * i + g;
-                if (okc[e] && row < nf && row >= col) dc[e][row] = cv[e][i] - acc[i][j][e];
+                // row group i = 2 * (m16 tile) + h  ->  acc[i >> 1][j][2 * (i & 1) + e]
+                if (okc[e] && row < nf && row >= col) dc[e][row] = cv[e][i] - acc[i >> 1][j][2 * (i & 1) + e];
             }
         }
     }
