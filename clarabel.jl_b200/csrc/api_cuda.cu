@@ -46,7 +46,11 @@ template <class T> struct DevBuf {
 
 struct Batch { int32_t off = 0, cnt = 0, maxnf = 0, maxns = 0, maxnr = 0, maxpanel = 0; bool many_children = false;
                int32_t schur_t128 = 0, schur_t64 = 0;
-               int32_t src_per_row = 0; };     // max over the fronts of (assembly sources / front rows)      // max over the fronts of the number of update-block tiles per side
+               int32_t src_per_row = 0;
+               bool all_padded = true;
+               std::vector<int32_t> ns_desc;  // large batches are sorted by pivot width (descending): the fronts still
+                                              // active at pivot column kb are the first active(kb) of the batch
+               int active(int kb) const { int c = 0; while (c < (int)ns_desc.size() && ns_desc[c] > kb) ++c; return c; } };     // every front of the batch is on the padded (TMA-addressable) layout     // max over the fronts of (assembly sources / front rows)      // max over the fronts of the number of update-block tiles per side
 
 constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
@@ -56,7 +60,6 @@ constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per s
 
 struct LevelPlan {
     Batch small[NSMALL];
-    Batch w32;                 // nf <= 32: warp-per-front register kernel (k_factor_warp32)
     Batch panel[NPANEL];       // 64 < nf <= 152: panel-in-smem kernel, classes by panel size
     Batch large;
     Batch solve[NSOLVE];
@@ -207,7 +210,10 @@ struct cb200_handle {
     bool to_large(int nf, int ns) const { return front_is_large(opt, nf, ns); }
     // TMA descriptors of the large-front panels (one CUtensorMap per large front)
     bool use_tma = false; int tma_kmajor = 1;
-    DevBuf<CUtensorMap> d_tmaps; DevBuf<int32_t> d_tmap_of;
+    int tma_tile = 64;                // CTA tile of the TMA GEMM: 64 (3 CTAs per SM; measured best on every workload:
+                                      // C5 Schur 5.4 ms against 8.4 with 128 and 7.5 with the LDG kernel, C4 32 / 42.5 / 42.9),
+                                      // 128, or 0 = by front size (CB200_TMA_TILE)
+    DevBuf<CUtensorMap> d_tmaps, d_tmaps64; DevBuf<int32_t> d_tmap_of;
     // multi-GPU state
     bool dist = false; int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -224,7 +230,14 @@ struct cb200_handle {
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool multi_stream = true;
-    bool use_warp32 = true;            // CB200_NO_WARP32=1: tiny fronts go back to k_factor_small
+    // bottom subtrees of narrow supernodes solved by one CTA each (k_fwd_subtree / k_bwd_subtree)
+    bool use_subtree = false;          // CB200_SUBTREE=1 turns them on.  Measured (C5): 5.58 ms per solve against 3.19 ms
+                                       // level-scheduled - with only L streamed from HBM but metadata still fetched per
+                                       // supernode, 16 warps per SM are too few to hide the dependent round trips.  Kept as
+                                       // the base of a version that bulk-prefetches the (contiguous) subtree panels.
+    int32_t nsub = 0, sub_nlev = 0, sub_maxcols = 0, sub_maxrows = 0;
+    DevBuf<int32_t> d_sub_sn0, d_sub_sn1, d_sub_order, d_sub_lvl;
+    DevBuf<int64_t> d_sub_optr;
     bool ms_on() const { return multi_stream && detail == 0; }
     void fork(int n) {            // side[0..n) start after everything issued so far on `stream`
         cudaEventRecord(ev_fork, stream);
@@ -401,7 +414,7 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
         { FineScope fs(h, Timers::F_BWD_WARP);
-        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), s_warp>>>(
+        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * (b1.maxnf + 32 + 32 * BT_LD) * sizeof(double), s_warp>>>(
             ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
         }
@@ -443,12 +456,13 @@ int build_tensor_maps(cb200_handle* h) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
         qres != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return 0; }
     EncodeTiledFn encode = (EncodeTiledFn)fn;
+    if (const char* e = getenv("CB200_TMA_TILE")) h->tma_tile = atoi(e);
     std::vector<int32_t> map_of(S.nsuper, -1);
-    std::vector<CUtensorMap> maps;
+    std::vector<CUtensorMap> maps, maps64;
     int kmajor = 1;
     if (const char* e = getenv("CB200_TMA_NATURAL")) if (e[0] == '1') kmajor = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        maps.clear(); std::fill(map_of.begin(), map_of.end(), -1);
+        maps.clear(); maps64.clear(); std::fill(map_of.begin(), map_of.end(), -1);
         bool ok = true;
         for (int32_t sn = 0; sn < S.nsuper && ok; ++sn) {
             const int ns = S.ns(sn), nf = ns + S.nr(sn);
@@ -464,16 +478,23 @@ int build_tensor_maps(cb200_handle* h) {
                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { ok = false; break; }
-            map_of[sn] = (int32_t)maps.size(); maps.push_back(m);
+            CUtensorMap m64;                              // same view, box of 64 rows for the small tile
+            if (kmajor) box[2] = 64 / 8; else box[1] = 64 / 8;
+            r = encode(&m64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)(h->d_L.p + S.panel_off[sn]), dims, strides,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { ok = false; break; }
+            map_of[sn] = (int32_t)maps.size(); maps.push_back(m); maps64.push_back(m64);
         }
         if (ok) { h->use_tma = true; h->tma_kmajor = kmajor; break; }
         if (kmajor == 0) break;
         kmajor = 0;                              // retry with the natural dimension order
     }
     if (!h->use_tma) return 0;
-    if (maps.empty()) maps.resize(1);
-    CUDA_OK(h->d_tmaps.alloc(maps.size()));
+    if (maps.empty()) { maps.resize(1); maps64.resize(1); }
+    CUDA_OK(h->d_tmaps.alloc(maps.size())); CUDA_OK(h->d_tmaps64.alloc(maps64.size()));
     CUDA_OK(cudaMemcpyAsync(h->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_tmaps64.p, maps64.data(), maps64.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h->d_tmap_of.upload(map_of, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -488,8 +509,12 @@ int build_plans(cb200_handle* h) {
     h->plan.assign(S.nlevels, LevelPlan());
     std::vector<int32_t> batches; std::vector<int64_t> woff;
     int64_t wmax = 0;
-    auto add_batch = [&](Batch& b, const std::vector<int32_t>& v, bool large, LevelPlan& P) {
+    auto add_batch = [&](Batch& b, std::vector<int32_t> v, bool large, LevelPlan& P) {
         b = Batch();
+        if (large) {
+            std::stable_sort(v.begin(), v.end(), [&](int32_t x, int32_t y) { return S.ns(x) > S.ns(y); });
+            for (int32_t sn : v) b.ns_desc.push_back(S.ns(sn));
+        }
         b.off = (int32_t)batches.size(); b.cnt = (int32_t)v.size();
         int64_t w = 0;
         for (int32_t sn : v) {
@@ -499,6 +524,7 @@ int build_plans(cb200_handle* h) {
             b.maxpanel = std::max(b.maxpanel, nf * S.ns(sn) + 25 * nf);      // smem need of k_factor_panel
             if (S.child_ptr[sn + 1] - S.child_ptr[sn] > 64) b.many_children = true;
             b.src_per_row = std::max<int32_t>(b.src_per_row, (int32_t)((S.asm_base[sn + 1] - S.asm_base[sn]) / std::max(1, nf)));
+            if (large && !h->to_large(nf, S.ns(sn))) b.all_padded = false;   // multi-GPU: small top fronts on the large path
             if (large && S.nr(sn) > 0) {
                 b.schur_t128 = std::max(b.schur_t128, (nf - 1) / TB - S.ns(sn) / TB + 1);
                 b.schur_t64 = std::max(b.schur_t64, (nf - 1) / GBM - S.ns(sn) / GBM + 1);
@@ -509,8 +535,57 @@ int build_plans(cb200_handle* h) {
         }
         if (large) { P.wtotal += w; wmax = std::max(wmax, w); }
     };
+    // ---- bottom subtrees for the solves: complete subtrees whose supernodes are all narrow (ns <= 32,
+    // nf <= SUB_MAXNF) and whose columns / contribution rows fit a shared-memory window
+    std::vector<int8_t> in_sub(S.nsuper, 0);
+    h->nsub = 0;
+    if (h->use_subtree && S.nsuper > 0) {
+        constexpr int64_t MAXCOLS = 2048, MAXROWS = 6144, MAXPANEL = 131072;
+        constexpr int32_t MINSN = 16;
+        const int32_t n = S.nsuper;
+        std::vector<int8_t> ok(n, 1);
+        std::vector<int64_t> wc(n), wr(n), wp(n); std::vector<int32_t> cnt(n, 1);
+        for (int32_t sn = 0; sn < n; ++sn) {            // children precede parents
+            const int64_t ns = S.ns(sn), nr = S.nr(sn);
+            wc[sn] += ns; wr[sn] += nr; wp[sn] += (ns + nr) * ns;
+            bool self = ns <= 32 && ns + nr <= SUB_MAXNF;
+            if (h->dist) self = self && !h->is_top[sn] && h->owner[sn] == h->rank;
+            if (!self || wc[sn] > MAXCOLS || wr[sn] > MAXROWS || wp[sn] > MAXPANEL) ok[sn] = 0;
+            const int32_t p = S.sn_parent[sn];
+            if (p >= 0) { wc[p] += wc[sn]; wr[p] += wr[sn]; wp[p] += wp[sn]; cnt[p] += cnt[sn]; if (!ok[sn]) ok[p] = 0; }
+        }
+        std::vector<int32_t> sn0, sn1, order, lvl; std::vector<int64_t> optr(1, 0);
+        int32_t maxl = 0;
+        std::vector<int32_t> roots;
+        for (int32_t sn = 0; sn < n; ++sn) {
+            const int32_t p = S.sn_parent[sn];
+            if (ok[sn] && (p < 0 || !ok[p]) && cnt[sn] >= MINSN) { roots.push_back(sn); maxl = std::max(maxl, S.sn_level[sn] + 1); }
+        }
+        h->sub_nlev = maxl; h->sub_maxcols = 1; h->sub_maxrows = 1;
+        for (int32_t r : roots) {
+            const int32_t a = r - cnt[r] + 1;
+            sn0.push_back(a); sn1.push_back(r);
+            h->sub_maxcols = std::max<int32_t>(h->sub_maxcols, (int32_t)wc[r]);
+            h->sub_maxrows = std::max<int32_t>(h->sub_maxrows, (int32_t)wr[r]);
+            std::vector<int32_t> off(maxl + 1, 0);
+            for (int32_t q = a; q <= r; ++q) { in_sub[q] = 1; off[S.sn_level[q] + 1]++; }
+            for (int32_t l = 0; l < maxl; ++l) off[l + 1] += off[l];
+            const size_t base = order.size();
+            order.resize(base + (size_t)cnt[r]);
+            { std::vector<int32_t> pos(off.begin(), off.end() - 1);
+              for (int32_t q = a; q <= r; ++q) order[base + pos[S.sn_level[q]]++] = q; }
+            lvl.insert(lvl.end(), off.begin(), off.end());
+            optr.push_back((int64_t)order.size());
+        }
+        h->nsub = (int32_t)roots.size();
+        if (h->nsub) {
+            CUDA_OK(h->d_sub_sn0.upload(sn0, s)); CUDA_OK(h->d_sub_sn1.upload(sn1, s));
+            CUDA_OK(h->d_sub_order.upload(order, s)); CUDA_OK(h->d_sub_lvl.upload(lvl, s));
+            CUDA_OK(h->d_sub_optr.upload(optr, s));
+        }
+    }
     for (int lv = 0; lv < S.nlevels; ++lv) {
-        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], pcl[NPANEL], top, w32;
+        std::vector<int32_t> cls[NSMALL + 1], scl[NSOLVE], pcl[NPANEL], top;
         for (int32_t q = S.level_ptr[lv]; q < S.level_ptr[lv + 1]; ++q) {
             int32_t sn = S.level_list[q];
             if (h->dist) {
@@ -520,8 +595,7 @@ int build_plans(cb200_handle* h) {
             int nf = S.ns(sn) + S.nr(sn);
             int c = 0; while (c < NSMALL && nf > kSmallNf[c]) ++c;
             if (h->to_large(nf, S.ns(sn)) || nf > kSmallNf[NSMALL - 1]) c = NSMALL;
-            if (h->use_warp32 && nf <= 32) w32.push_back(sn);
-            else if (h->to_panel(nf, S.ns(sn))) {
+            if (h->to_panel(nf, S.ns(sn))) {
                 int pc = 0; while (nf * S.ns(sn) + 25 * nf > kPanelDoubles[pc]) ++pc;
                 pcl[pc].push_back(sn);
             } else cls[c].push_back(sn);
@@ -529,12 +603,11 @@ int build_plans(cb200_handle* h) {
             const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
             const bool tiny = S.ns(sn) <= SG && nf <= 32;
             const int d = leaf ? 0 : (tiny ? 4 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2)));
-            scl[d].push_back(sn);
+            if (!in_sub[sn]) scl[d].push_back(sn);
         }
         LevelPlan& P = h->plan[lv];
         P.wtotal = 0;
         for (int c = 0; c < NSMALL; ++c) add_batch(P.small[c], cls[c], false, P);
-        add_batch(P.w32, w32, false, P);
         for (int c = 0; c < NPANEL; ++c) add_batch(P.panel[c], pcl[c], false, P);
         add_batch(P.large, cls[NSMALL], true, P);
         for (int d = 0; d < NSOLVE; ++d) add_batch(P.solve[d], scl[d], false, P);
@@ -639,18 +712,11 @@ int factor_body(cb200_handle* h, bool static_reg) {
         bool small_work = false;
         for (int c = 0; c < NSMALL; ++c) small_work |= P.small[c].cnt != 0;
         for (int c = 0; c < NPANEL; ++c) small_work |= P.panel[c].cnt != 0;
-        small_work |= P.w32.cnt != 0;
         // the small-front kernels of a level run beside the pivot-block chain of its large fronts
         const bool ms = h->ms_on() && small_work && (P.large.cnt || P.topf.cnt);
         cudaStream_t ss = ms ? h->side[0] : st;
         if (ms) h->fork(1);
         if (h->detail) h->tm.begin(Timers::SMALL, st);
-        if (P.w32.cnt) {
-            FineScope fs(h, Timers::F_SMALL0);
-            k_factor_warp32<<<nblk(P.w32.cnt, 8), 256, (size_t)8 * 32 * FW_LD * sizeof(double), ss>>>(
-                ds, h->d_batches.p + P.w32.off, P.w32.cnt, h->d_L.p, h->d_U.p, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
-            LAUNCH(h);
-        }
         launch_small<32>(h, P.small[0], 0, rp, ss);        // size classes kSmallNf[0..5]
         launch_small<64>(h, P.small[1], 1, rp, ss);
         launch_small<128>(h, P.small[2], 2, rp, ss);
@@ -697,7 +763,8 @@ int factor_body(cb200_handle* h, bool static_reg) {
             const size_t smrows = (size_t)(2 * PB * (PB + 1)) * sizeof(double);
             // one update launch (either version): mode 0 = panel step at pivot block J0, mode 1 = Schur
             auto launch_update = [&](int mode, int J0) {
-                const int T = h->use_tma ? TB : GBM;
+                const bool tma = h->use_tma && B.all_padded;
+                const int T = !tma ? GBM : (h->tma_tile == 64 || h->tma_tile == 128 ? h->tma_tile : (B.maxnf >= 1024 ? 128 : 64));
                 int gx, na = 1;
                 if (mode == 0) {
                     const int tj0 = (J0 + PB) / T;
@@ -706,25 +773,32 @@ int factor_body(cb200_handle* h, bool static_reg) {
                     if (nbt <= 0 || na <= 0) return;
                     gx = nbt * na;
                 } else {
-                    const int t = h->use_tma ? B.schur_t128 : B.schur_t64;
+                    const int t = T == 128 ? B.schur_t128 : B.schur_t64;
                     if (t <= 0) return;
                     gx = t * (t + 1) / 2;
                 }
-                if (h->use_tma)
-                    k_ldl_update_tma<<<dim3(gx, B.cnt), TMA_THREADS, TMA_GEMM_SMEM, st>>>(
+                const int ny = mode == 0 ? B.active(J0 + PB) : B.cnt;     // fronts that still have panel columns to update
+                if (ny <= 0) return;
+                if (tma && T == 128)
+                    k_ldl_update_tma<128><<<dim3(gx, ny), tma_threads(128), tma_gemm_smem(128), st>>>(
                         ds, bl, h->d_tmaps.p, h->d_tmap_of.p, mode, J0, na, h->tma_kmajor, h->d_L.p, h->d_U.p, h->d_D.p);
+                else if (tma)
+                    k_ldl_update_tma<64><<<dim3(gx, ny), tma_threads(64), tma_gemm_smem(64), st>>>(
+                        ds, bl, h->d_tmaps64.p, h->d_tmap_of.p, mode, J0, na, h->tma_kmajor, h->d_L.p, h->d_U.p, h->d_D.p);
                 else
-                    k_ldl_update_ldg<<<dim3(gx, B.cnt), 256, 0, st>>>(ds, bl, mode, J0, na, h->d_L.p, h->d_U.p, h->d_D.p);
+                    k_ldl_update_ldg<<<dim3(gx, ny), 256, 0, st>>>(ds, bl, mode, J0, na, h->d_L.p, h->d_U.p, h->d_D.p);
                 LAUNCH(h);
             };
             for (int kb = 0; kb < B.maxns; kb += PB) {
+                const int nact = B.active(kb);
+                if (nact <= 0) break;
                 { FineScope fs(h, Timers::F_DIAG);
-                  k_piv_diag<<<B.cnt, 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
+                  k_piv_diag<<<nact, 256, 0, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_D.p, h->d_Dinv.p, rp, h->d_nreg.p);
                   LAUNCH(h); }
                 const int rows_below = B.maxnf - kb - 1;
                 if (rows_below > 0) {
                     FineScope fs(h, Timers::F_ROWS);
-                    k_piv_rows<<<dim3(nblk(rows_below, GBM), B.cnt), 256, smrows, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_Dinv.p);
+                    k_piv_rows<<<dim3(nblk(rows_below, GBM), nact), 256, smrows, st>>>(ds, bl, kb, h->d_L.p, h->d_W.p, wo, h->d_Dinv.p);
                     LAUNCH(h);
                 }
                 if (kb + PB < B.maxns) { FineScope fs(h, Timers::F_PANELUPD); launch_update(0, kb); }
@@ -751,10 +825,29 @@ int factor(cb200_handle* h, bool static_reg) {
 }
 
 // y (permuted, in d_y) <- K^-1 : forward, diagonal, backward
+SubTrees subtrees(cb200_handle* h) {
+    SubTrees T;
+    T.sn0 = h->d_sub_sn0.p; T.sn1 = h->d_sub_sn1.p; T.order = h->d_sub_order.p; T.order_ptr = h->d_sub_optr.p;
+    T.lvl_off = h->d_sub_lvl.p; T.nlev = h->sub_nlev; T.maxcols = h->sub_maxcols; T.maxrows = h->sub_maxrows;
+    return T;
+}
+size_t subtree_smem_fwd(const cb200_handle* h) { return ((size_t)h->sub_maxcols + h->sub_maxrows + 8 * SUB_MAXNF) * sizeof(double); }
+size_t subtree_smem_bwd(const cb200_handle* h) { return ((size_t)h->sub_maxcols + 8 * (SUB_MAXNF + 32 * BT_LD)) * sizeof(double); }
+
 int sweeps_body(cb200_handle* h) {
     const auto& S = h->S;
+    if (h->nsub) {        // the bottom subtrees first: everything above them depends on their contributions
+        FineScope fs(h, Timers::F_FWD_SUB);
+        k_fwd_subtree<<<h->nsub, 256, subtree_smem_fwd(h), h->stream>>>(devsym(h), subtrees(h), h->d_L.p, h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
+    }
     for (int lv = 0; lv < S.nlevels; ++lv) launch_fwd_level(h, h->plan[lv], lv);
     for (int lv = S.nlevels - 1; lv >= 0; --lv) launch_bwd_level(h, h->plan[lv]);
+    if (h->nsub) {
+        FineScope fs(h, Timers::F_BWD_SUB);
+        k_bwd_subtree<<<h->nsub, 256, subtree_smem_bwd(h), h->stream>>>(devsym(h), subtrees(h), h->d_L.p, h->d_Dinv.p, h->d_y.p);
+        LAUNCH(h);
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -897,7 +990,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         }
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         if (const char* e = getenv("CB200_MULTISTREAM")) h->multi_stream = e[0] != '0';
-        if (const char* e = getenv("CB200_NO_WARP32")) h->use_warp32 = e[0] != '1';
+        if (const char* e = getenv("CB200_SUBTREE")) h->use_subtree = e[0] == '1';
         cudaStream_t s = h->stream;
         // ---- K
         std::vector<int32_t> ri32(ri.begin(), ri.end());
@@ -971,9 +1064,12 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
                                      (32 * 32 + SB * SB) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_piv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * PB * (PB + 1)) * (int)sizeof(double)));
-        CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_GEMM_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_gemm_smem(128)));
+        CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_gemm_smem(64)));
         { int rct = build_tensor_maps(h); if (rct) return rct; }
-        CUDA_OK(cudaFuncSetAttribute(k_factor_warp32, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * FW_LD * (int)sizeof(double)));
+        CUDA_OK(cudaFuncSetAttribute(k_fwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); return -4; }

@@ -156,116 +156,6 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
     }
 }
 
-// ------------------------------------------------------------------ G4w tiny fronts (nf <= 32): warp per front
-// One warp per front, 8 fronts per CTA, no barrier anywhere.  The front is staged in a per-warp
-// shared-memory tile (coalesced panel read, extend-add through the destination-owner lists: fixed
-// summation order), then lane j takes COLUMN j into registers (a[i] = F[i][j]).  With column
-// ownership the pivot loop runs over a RUNTIME k with only static register indices (a fully
-// unrolled row-ownership version was 20x slower: instruction-cache bound):
-//   LDL'   step k: column k is broadcast by shuffles, d_k gets the sign-based dynamic regularisation
-//          (QDLDL rule), lane j > k applies a[i] -= A[i][k] A[j][k] / d_k to its column
-//   X = inv(L11) in place: acc = -L[:,j]; step k: lanes j < k add L[:,k] X[k][j]  (at step k column k
-//          still holds -L[:,k] untouched, X[k][j] is final)
-// This is the kernel the subtree collapse of the symbolic analysis feeds: ~5e5 fronts on C5.
-constexpr int FW_LD = 33;
-__global__ void __launch_bounds__(256)
-k_factor_warp32(DevSym S, const int32_t* __restrict__ batch, int count, double* __restrict__ Lst,
-                double* __restrict__ Ust, double* __restrict__ D, double* __restrict__ Dinv,
-                RegParams rp, unsigned int* __restrict__ nreg) {
-    extern __shared__ double fw_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 8 + wid;
-    if (idx >= count) return;
-    const int s = batch[idx];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-    const int nf = ns + nr;
-    double* Lp = Lst + S.panel_off[s];
-    double* F = fw_smem + (size_t)wid * (32 * FW_LD);          // F[i + j*FW_LD], column-major
-    for (int e = lane; e < 32 * FW_LD; e += 32) F[e] = 0.0;
-    __syncwarp();
-    for (int j = 0; j < ns; ++j) if (lane < nf) F[lane + j * FW_LD] = Lp[j * nf + lane];
-    __syncwarp();
-    if (S.child_ptr[s + 1] != S.child_ptr[s]) {
-        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
-        const int64_t base = S.asm_base[s];
-        for (int d = 0; d < nf; ++d) {
-            double* dst = F + d * FW_LD;
-            for (int e = cp[d]; e < cp[d + 1]; ++e) {
-                const int q = S.asm_src[base + e];
-                const int c = S.asm_child[base + e];
-                const int64_t rp0 = S.rows_ptr[c];
-                const int nrc = (int)(S.rows_ptr[c + 1] - rp0);
-                const int jc = (int)(q - rp0);
-                const int32_t* relc = S.rel + rp0;
-                const double* src = Ust + S.upd_off[c] + (int64_t)jc * nrc;
-                for (int i2 = jc + lane; i2 < nrc; i2 += 32) dst[relc[i2]] += src[i2];
-                __syncwarp();
-            }
-        }
-    }
-    double a[32];                                   // column `lane` of the front (rows i >= lane matter)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = (i >= lane) ? F[i + lane * FW_LD] : 0.0;
-    // ---- LDL'
-    unsigned int myreg = 0;
-    double dmine = 1.0, dimine = 1.0;               // lane k keeps d_k and 1/d_k
-    for (int k = 0; k < ns; ++k) {
-        double c[32];
-        double d = 0.0, cj = 0.0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            c[i] = __shfl_sync(0xffffffffu, a[i], k);             // A[i][k] (i >= k)
-            if (i == k) d = c[i];
-            if (i == lane) cj = c[i];
-        }
-        const double sg = (double)S.dsign[f + k];
-        if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; if (lane == 0) ++myreg; }
-        const double dinv = 1.0 / d;
-        if (lane > k) {
-            const double wj = cj * dinv;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (i >= lane) a[i] -= c[i] * wj;
-        } else if (lane == k) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { if (i > k) a[i] = c[i] * dinv; else if (i == k) a[i] = d; }
-            dmine = d; dimine = dinv;
-        }
-    }
-    if (lane < ns) { D[f + lane] = dmine; Dinv[f + lane] = dimine; }
-    if (lane == 0 && myreg) atomicAdd(nreg, myreg);
-    // ---- X = inv(L11): lane j < ns works on rows j < i < ns of its column; the rows i >= ns (L21) stay
-    if (ns > 1) {
-        // in place: rows lane < i < ns of a[] hold -L[i][lane] and turn into X[i][lane]
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (i > lane && i < ns) a[i] = -a[i];
-        for (int k = 1; k < ns; ++k) {
-            double xk = 0.0;
-            double c[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                c[i] = __shfl_sync(0xffffffffu, a[i], k);         // -L[i][k] for k < i < ns (untouched so far)
-                if (i == k) xk = a[i];                            // X[k][lane], final for lane < k
-            }
-            if (lane < k) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i > k && i < ns) a[i] += c[i] * xk;
-            }
-        }
-    }
-    // ---- write back through the tile (coalesced global stores)
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) if (i >= lane) F[i + lane * FW_LD] = a[i];
-    __syncwarp();
-    for (int j = 0; j < ns; ++j) if (lane >= j && lane < nf) Lp[j * nf + lane] = F[lane + j * FW_LD];
-    if (nr > 0) {
-        double* Us = Ust + S.upd_off[s];
-        for (int j = ns; j < nf; ++j) if (lane >= j && lane < nf) Us[(lane - ns) + (int64_t)(j - ns) * nr] = F[lane + j * FW_LD];
-    }
-}
-
 // ------------------------------------------------------------------ G4b mid-size fronts (64 < nf <= 152)
 // Only the nf x ns panel lives in shared memory (a front of 128 x 30 needs 31 KB instead of
 // 128 KB => several CTAs per SM); the update block stays in global memory:
@@ -724,12 +614,13 @@ k_ldl_update_ldg(DevSym S, const int32_t* __restrict__ batch, int mode, int J0, 
 }
 
 // ---- TMA-fed version -------------------------------------------------------------------------
-constexpr int TB = 128;                         // CTA tile (rows and columns)
+constexpr int TB = 128;                         // large CTA tile (rows and columns); the small one is 64
 constexpr int TK = 16;                          // k-slab per pipeline stage
 constexpr int TSTAGES = 4;
-constexpr int TMA_THREADS = 288;                // 8 consumer warps + 1 producer warp
-constexpr int TTILE = TB * TK;                  // doubles per operand per stage (16 KB)
-constexpr size_t TMA_GEMM_SMEM = (size_t)TSTAGES * 2 * TTILE * sizeof(double) + 2 * TSTAGES * sizeof(uint64_t);
+// tile T x T: consumer warps (T/64 x T/32 for T = 128: warp tile 64 x 32; 2 x 2 for T = 64: warp tile 32 x 32)
+// plus one producer warp
+constexpr int tma_threads(int T) { return (T == 128 ? 8 : 4) * 32 + 32; }
+constexpr size_t tma_gemm_smem(int T) { return (size_t)TSTAGES * 2 * T * TK * sizeof(double) + 2 * TSTAGES * sizeof(uint64_t); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -761,7 +652,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // fragment load read 32 consecutive doubles (conflict-free).  If the driver rejects that dimension
 // order the natural one (8 rows, row-groups, k) is used: layout [k][row-group][8], strides passed in
 // (sk, srg) - same kernel, 4-way bank conflicts on the fragment loads.
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+template <int T>
+__global__ void __launch_bounds__(tma_threads(T), T == 128 ? 1 : 3)
 k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap* __restrict__ maps,
                  const int32_t* __restrict__ map_of, int mode, int J0, int na, int kmajor,
                  double* __restrict__ Lst, double* __restrict__ Ust, const double* __restrict__ D) {
@@ -772,9 +664,13 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
     const int nr = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
     const int nf = ns + nr;
     const int ld = S.ld[s];
-    const UpdTile u = decode_update_tile<TB>(mode, J0, na, ns, nf);
+    const UpdTile u = decode_update_tile<T>(mode, J0, na, ns, nf);
     if (!u.valid) return;
     double* sA = reinterpret_cast<double*>(tma_smem);
+    constexpr int TTILE = T * TK;                      // doubles per operand per stage
+    constexpr int NCW = T == 128 ? 8 : 4;              // consumer warps
+    constexpr int WM = T == 128 ? 64 : 32, WN = 32;    // warp tile
+    constexpr int MI = WM / 16, NJ = WN / 8;
     double* sB = sA + TSTAGES * TTILE;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + TSTAGES * TTILE);
     uint64_t* empty = full + TSTAGES;
@@ -782,11 +678,11 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
     const int nk = (u.k1 - u.k0 + TK - 1) / TK;
     if (tid == 0) {
 #pragma unroll
-        for (int st = 0; st < TSTAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, 8); }
+        for (int st = 0; st < TSTAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    if (wid == 8) {
+    if (wid == NCW) {
         // ===== TMA producer (one lane) =====
         if (lane == 0) {
             const CUtensorMap* tm = maps + map_of[s];
@@ -797,26 +693,26 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
                 mbar_expect_tx(full + st, 2u * TTILE * (uint32_t)sizeof(double));
                 const int kc = u.k0 + it * TK;
                 if (kmajor) {
-                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, kc, u.ti * (TB / 8));
-                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, kc, u.tj * (TB / 8));
+                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, kc, u.ti * (T / 8));
+                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, kc, u.tj * (T / 8));
                 } else {
-                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, u.ti * (TB / 8), kc);
-                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, u.tj * (TB / 8), kc);
+                    tma_load_3d(sA + st * TTILE, tm, full + st, 0, u.ti * (T / 8), kc);
+                    tma_load_3d(sB + st * TTILE, tm, full + st, 0, u.tj * (T / 8), kc);
                 }
             }
         }
         return;
     }
     // ===== 8 consumer warps (2 x 4), warp tile 64 x 32 = 4 x 4 DMMA m16n8k16 tiles per k-slab =====
-    const int sk = kmajor ? 8 : TB, srg = kmajor ? TK * 8 : 8;      // strides (doubles) of k and of a row-group
-    const int wm = (wid & 1) * 64, wn = (wid >> 1) * 32;
+    const int sk = kmajor ? 8 : T, srg = kmajor ? TK * 8 : 8;       // strides (doubles) of k and of a row-group
+    const int wm = (wid & 1) * WM, wn = (wid >> 1) * WN;
     const int g = lane >> 2, t = lane & 3;
     const double* Dv = D + f;
-    double acc[4][4][4];
+    double acc[MI][NJ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
     for (int it = 0; it < nk; ++it) {
@@ -828,20 +724,20 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
         mbar_wait(full + st, ph);
         const double* A = sA + st * TTILE + (wm / 8) * srg + g;
         const double* B = sB + st * TTILE + (wn / 8) * srg + g;
-        double bf[4][4];
+        double bf[NJ][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int v = 0; v < 4; ++v) bf[j][v] = B[j * srg + (4 * v + t) * sk] * dv[v];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MI; ++i) {
             double af[8];
 #pragma unroll
             for (int v = 0; v < 4; ++v)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) af[2 * v + h] = A[(2 * i + h) * srg + (4 * v + t) * sk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma16816(acc[i][j], af, bf[j]);
+            for (int j = 0; j < NJ; ++j) dmma16816(acc[i][j], af, bf[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
@@ -851,27 +747,27 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
     double* Lp = Lst + S.panel_off[s];
     double* Us = Ust + S.upd_off[s];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double cv[2][8];
+    for (int j = 0; j < NJ; ++j) {
+        double cv[2][2 * MI];
         double* dc[2];
         bool okc[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int col = u.tj * TB + wn + 8 * j + 2 * t + e;
+            const int col = u.tj * T + wn + 8 * j + 2 * t + e;
             okc[e] = col >= u.c_lo && col < u.c_hi;
             dc[e] = col < ns ? Lp + (int64_t)col * ld : Us + (int64_t)(col - ns) * nr - ns;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = u.ti * TB + wm + 8 * i + g;
+            for (int i = 0; i < 2 * MI; ++i) {
+                const int row = u.ti * T + wm + 8 * i + g;
                 cv[e][i] = (okc[e] && row < nf && row >= col) ? dc[e][row] : 0.0;
             }
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int col = u.tj * TB + wn + 8 * j + 2 * t + e;
+            const int col = u.tj * T + wn + 8 * j + 2 * t + e;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = u.ti * TB + wm + 8 * i + g;
+            for (int i = 0; i < 2 * MI; ++i) {
+                const int row = u.ti * T + wm + 8 * i + g;
                 // row group i = 2 * (m16 tile) + h  ->  acc[i >> 1][j][2 * (i & 1) + e]
                 if (okc[e] && row < nf && row >= col) dc[e][row] = cv[e][i] - acc[i >> 1][j][2 * (i & 1) + e];
             }
@@ -986,7 +882,7 @@ k_piv_rows(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restri
     const int r0 = J0 + nb + blockIdx.x * GBM;
     if (r0 >= nf) return;
     double* Lp = Lst + S.panel_off[s];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x;
     for (int e = tid; e < PB * PB; e += 256) {
         const int i = e & (PB - 1), k = e >> 6;
         const int gr = r0 + i;
@@ -1003,35 +899,41 @@ k_piv_rows(DevSym S, const int32_t* __restrict__ batch, int J0, double* __restri
         Ms[kk * (PB + 1) + jj] = v;                  // M[k][j] = inv(L)[j][k] * dinv[j], k <= j
     }
     __syncthreads();
-    // L[rows, J] = T * M : out[i][j] = sum_{k <= j} T[i][k] M[k][j]
-    double out[4][4];
+    // L[rows, J] = T * M : out[i][j] = sum_{k <= j} T[i][k] M[k][j]  on the FP64 tensor-core path
+    // (8 warps as 2 x 4, warp tile 32 x 16 = 4 x 2 DMMA fragments, K = 64)
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wm = (wid & 1) * 32, wn = (wid >> 1) * 16;
+    const int g = lane >> 2, t = lane & 3;
+    double cf[4][2][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) out[a][c] = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < PB; ++k) {
-        double tv[4], mv[4];
+        for (int j = 0; j < 2; ++j) { cf[i][j][0] = 0.0; cf[i][j][1] = 0.0; }
+#pragma unroll 4
+    for (int k4 = 0; k4 < PB; k4 += 4) {
+        double af[4], bf[2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) tv[a] = Ts[(tx * 4 + a) * (PB + 1) + k];
+        for (int i = 0; i < 4; ++i) af[i] = Ts[(wm + 8 * i + g) * (PB + 1) + k4 + t];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mv[c] = Ms[k * (PB + 1) + ty * 4 + c];
+        for (int j = 0; j < 2; ++j) bf[j] = Ms[(k4 + t) * (PB + 1) + wn + 8 * j + g];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) out[a][c] += tv[a] * mv[c];
+            for (int j = 0; j < 2; ++j) dmma884(cf[i][j][0], cf[i][j][1], af[i], bf[j]);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int j = ty * 4 + c;
-        if (j >= nb) continue;
-        double* col = Lp + (int64_t)(J0 + j) * ld;
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int gr = r0 + tx * 4 + a;
-            if (gr < nf) col[gr] = out[a][c];
+        for (int e = 0; e < 2; ++e) {
+            const int col = wn + 8 * j + 2 * t + e;
+            if (col >= nb) continue;
+            double* cp_ = Lp + (int64_t)(J0 + col) * ld;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int gr = r0 + wm + 8 * i + g;
+                if (gr < nf) cp_[gr] = cf[i][j][e];
+            }
         }
-    }
 }
 
 // Finish the large fronts of a level: copy the parked blocks [inv(L_JJ) strictly lower ; d on the
@@ -1235,15 +1137,11 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&p)[32], int lan
     return p[0];
 }
 
-__global__ void __launch_bounds__(WPB * 32, 2)
-k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
-           const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int idx = blockIdx.x * WPB + wid;
-    if (idx >= count) return;
-    double* w = smem + (size_t)wid * maxnf;
-    const int s = batch[idx];
+// Forward step of one narrow supernode by one warp.  Y / U are the solution / contribution vectors
+// addressed with GLOBAL indices: in the level-scheduled kernels they are the global arrays, in the
+// subtree kernels they are shared-memory windows shifted by the window origin.
+__device__ __forceinline__ void fwd_warp_body(const DevSym& S, int s, const double* __restrict__ Lst,
+                                              double* Y, double* U, double* w, int lane) {
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
     const int64_t rp = S.rows_ptr[s];
@@ -1259,8 +1157,8 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
         const int32_t* cp = S.asm_colptr + S.front_ptr[s];
         const int64_t base = S.asm_base[s];
         for (int i = lane; i < nf; i += 32) {
-            double acc = i < ns ? y[f + i] : 0.0;
-            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
+            double acc = i < ns ? Y[f + i] : 0.0;
+            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += U[S.asm_src[base + e]];
             w[i] = acc;
         }
     }
@@ -1270,7 +1168,7 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
 #pragma unroll
     for (int j = 0; j < 32; ++j) if (j < ns) xi += v[j] * w[j];
     __syncwarp();
-    if (lane < ns) { w[lane] = xi; y[f + lane] = xi; }
+    if (lane < ns) { w[lane] = xi; Y[f + lane] = xi; }
     __syncwarp();
     // u = w_bot - L21 x : one row per lane, all ns column loads of a row in flight together
     for (int r = ns + lane; r < nf; r += 32) {
@@ -1279,8 +1177,73 @@ k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
-        uvec[rp + r - ns] = w[r] - (a0 + a1);
+        U[rp + r - ns] = w[r] - (a0 + a1);
     }
+}
+
+// Backward step of one narrow supernode by one warp.  Columns in [win_lo, win_hi) are read from the
+// window Y, all others (ancestors outside a subtree) from the global solution vector yg.
+// The transposed products go through a 32 x 33 shared tile (coalesced loads by rows, conflict-free
+// reads by columns) instead of shuffle reductions: inside the loops of the subtree kernel the compiler
+// cannot prove warp convergence and wraps every shuffle in WARPSYNC.COLLECTIVE (~50 cycles each).
+constexpr int BT_LD = 33;
+__device__ __forceinline__ void bwd_warp_body(const DevSym& S, int s, const double* __restrict__ Lst,
+                                              const double* __restrict__ Dinv, double* Y, const double* yg,
+                                              int win_lo, int win_hi, double* w, double* tile, int lane) {
+    const int f = S.sn_first[s];
+    const int ns = S.sn_first[s + 1] - f;
+    const int64_t rp = S.rows_ptr[s];
+    const int nr = (int)(S.rows_ptr[s + 1] - rp);
+    const int nf = ns + nr;
+    const int ld = S.ld[s];
+    const double* Lp = Lst + S.panel_off[s];
+    // the triangle (row `lane`): X[lane][j], j < lane - independent of the gather below
+    double xr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xr[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    for (int i = lane; i < nf; i += 32) {
+        double val;
+        if (i < ns) val = Y[f + i] * Dinv[f + i];
+        else { const int c = S.rows[rp + i - ns]; val = (c >= win_lo && c < win_hi) ? Y[c] : yg[c]; }
+        w[i] = val;
+    }
+    __syncwarp();
+    // t_j = w_j - sum_{r >= ns} L[r][j] w_r   (lane j owns column j)
+    double acc = 0.0;
+    for (int r0 = ns; r0 < nf; r0 += 32) {
+        const int r = r0 + lane;
+        double v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j < ns && r < nf) ? Lp[(int64_t)j * ld + r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile[lane * BT_LD + j] = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) { const double wr = (r0 + rr < nf) ? w[r0 + rr] : 0.0; acc += tile[rr * BT_LD + lane] * wr; }
+        __syncwarp();
+    }
+    const double tj = (lane < ns) ? w[lane] - acc : 0.0;
+    // x_j = t_j + sum_{i>j} X[i][j] t_i
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tile[lane * BT_LD + j] = xr[j];
+    __syncwarp();                                  // everyone has read w[0..ns) above
+    if (lane < 32) w[lane] = tj;                   // t (zero beyond ns)
+    __syncwarp();
+    double corr = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) corr += tile[i * BT_LD + lane] * w[i];
+    if (lane < ns) Y[f + lane] = tj + corr;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(WPB * 32, 2)
+k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
+           const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int idx = blockIdx.x * WPB + wid;
+    if (idx >= count) return;
+    fwd_warp_body(S, batch[idx], Lst, y, uvec, smem + (size_t)wid * maxnf, lane);
 }
 
 __global__ void __launch_bounds__(WPB * 32, 2)
@@ -1290,40 +1253,83 @@ k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int idx = blockIdx.x * WPB + wid;
     if (idx >= count) return;
-    double* w = smem + (size_t)wid * maxnf;
-    const int s = batch[idx];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    const int ld = S.ld[s];
-    const double* Lp = Lst + S.panel_off[s];
-    for (int i = lane; i < nf; i += 32) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
-    __syncwarp();
-    // t_j = w_j - sum_{r >= ns} L[r][j] w_r : lane owns rows r, keeps one partial sum per column j
-    double p[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) p[j] = 0.0;
-    for (int r = ns + lane; r < nf; r += 32) {
-        double v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
-        const double wr = w[r];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) p[j] += v[j] * wr;
+    double* base = smem + (size_t)wid * (maxnf + 32 + 32 * BT_LD);       // w (padded to >= 32) then the tile
+    bwd_warp_body(S, batch[idx], Lst, Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
+}
+
+// --- whole subtrees of narrow supernodes: one CTA per subtree, no level barrier across the grid.
+// The bottom of the assembly tree holds > 99 % of the supernodes; level-scheduled launches make every
+// one of them pay a chain of dependent global round trips per sweep with only a wave of warps in
+// flight.  Here a CTA owns a complete subtree (contiguous in postorder => contiguous columns, rows,
+// panels): its slice of the solution and of the children-contribution vector live in SHARED memory
+// for the whole sweep, the warps walk the subtree level by level (block barriers only), and only L is
+// streamed from HBM.  Deterministic (same arithmetic as the level-scheduled kernels).
+struct SubTrees {
+    const int32_t* sn0;        // [nsub] first supernode of the subtree
+    const int32_t* sn1;        // [nsub] its root (last supernode)
+    const int32_t* order;      // supernodes of all subtrees, per subtree sorted by level
+    const int64_t* order_ptr;  // [nsub+1]
+    const int32_t* lvl_off;    // [nsub * (nlev+1)] offsets into the subtree's slice of `order`
+    int32_t nlev;              // levels a subtree can span
+    int32_t maxcols, maxrows;  // window sizes (doubles) the shared memory is dimensioned for
+};
+constexpr int SUB_MAXNF = 192;
+
+__global__ void __launch_bounds__(256, 2)
+k_fwd_subtree(DevSym S, SubTrees T, const double* __restrict__ Lst, double* __restrict__ y,
+              double* __restrict__ uvec) {
+    extern __shared__ double smem[];
+    double* ysm = smem;
+    double* usm = ysm + T.maxcols;
+    double* wsm = usm + T.maxrows;
+    const int t = blockIdx.x;
+    const int a = T.sn0[t], b = T.sn1[t];
+    const int col_lo = S.sn_first[a], col_hi = S.sn_first[b + 1];
+    const int64_t u_lo = S.rows_ptr[a];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < col_hi - col_lo; i += 256) ysm[i] = y[col_lo + i];
+    __syncthreads();
+    double* Y = ysm - col_lo;
+    double* U = usm - u_lo;
+    const int32_t* ord = T.order + T.order_ptr[t];
+    const int32_t* lo = T.lvl_off + (int64_t)t * (T.nlev + 1);
+    double* w = wsm + wid * SUB_MAXNF;
+    for (int l = 0; l < T.nlev; ++l) {
+        const int e0 = lo[l], e1 = lo[l + 1];
+        if (e0 == e1) continue;                                // (uniform) nothing on this level
+        for (int k = e0 + wid; k < e1; k += 8) fwd_warp_body(S, ord[k], Lst, Y, U, w, lane);
+        __syncthreads();
     }
-    // the triangle (row `lane`): X[lane][j], j < lane - issued before the reduction shuffles
-    double xr[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) xr[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
-    const double red = warp_transpose_reduce(p, lane);
-    const double tj = (lane < ns) ? w[lane] - red : 0.0;
-    // x_j = t_j + sum_{i>j} X[i][j] t_i : lane i contributes X[i][j] t_i to column j
-#pragma unroll
-    for (int j = 0; j < 32; ++j) p[j] = xr[j] * tj;
-    const double corr = warp_transpose_reduce(p, lane);
-    if (lane < ns) y[f + lane] = tj + corr;
+    for (int i = tid; i < col_hi - col_lo; i += 256) y[col_lo + i] = ysm[i];
+    // only the root's contribution leaves the subtree
+    const int64_t r0 = S.rows_ptr[b], r1 = S.rows_ptr[b + 1];
+    for (int64_t q = r0 + tid; q < r1; q += 256) uvec[q] = usm[q - u_lo];
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_bwd_subtree(DevSym S, SubTrees T, const double* __restrict__ Lst, const double* __restrict__ Dinv,
+              double* __restrict__ y) {
+    extern __shared__ double smem[];
+    double* ysm = smem;
+    double* wsm = ysm + T.maxcols;
+    const int t = blockIdx.x;
+    const int a = T.sn0[t], b = T.sn1[t];
+    const int col_lo = S.sn_first[a], col_hi = S.sn_first[b + 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < col_hi - col_lo; i += 256) ysm[i] = y[col_lo + i];
+    __syncthreads();
+    double* Y = ysm - col_lo;
+    const int32_t* ord = T.order + T.order_ptr[t];
+    const int32_t* lo = T.lvl_off + (int64_t)t * (T.nlev + 1);
+    double* w = wsm + wid * (SUB_MAXNF + 32 * BT_LD);
+    double* tile = w + SUB_MAXNF;
+    for (int l = T.nlev - 1; l >= 0; --l) {
+        const int e0 = lo[l], e1 = lo[l + 1];
+        if (e0 == e1) continue;
+        for (int k = e0 + wid; k < e1; k += 8) bwd_warp_body(S, ord[k], Lst, Dinv, Y, y, col_lo, col_hi, w, tile, lane);
+        __syncthreads();
+    }
+    for (int i = tid; i < col_hi - col_lo; i += 256) y[col_lo + i] = ysm[i];
 }
 
 // --- tiny supernodes (ns <= 8, nf <= 32, with children): 8 lanes per supernode, 32 supernodes
