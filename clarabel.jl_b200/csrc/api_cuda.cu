@@ -56,7 +56,8 @@ constexpr int NSMALL = 6;
 static const int kSmallNf[NSMALL] = {16, 32, 64, 96, 128, 152};
 constexpr int NPANEL = 4;
 static const int kPanelDoubles[NPANEL] = {4096, 9000, 16000, 1 << 30};   // smem need classes (doubles)
-constexpr int NSOLVE = 5;      // 0: single-column leaves, 1: warp, 2: CTA per supernode, 3: multi-CTA (big), 4: 8 lanes (tiny)
+constexpr int NSOLVE = 6;      // 0: single-column leaves, 1: warp (16 < ns <= 32), 2: CTA per supernode, 3: multi-CTA (big),
+                               // 4: 8 lanes (tiny), 5: warp, ns <= 16 (half the registers, twice the warps in flight)
 
 struct LevelPlan {
     Batch small[NSMALL];
@@ -165,13 +166,14 @@ struct cb200_handle {
     DevBuf<int32_t> d_perm;
     // symbolic
     DevBuf<int32_t> d_sn_first, d_rows, d_rel, d_child_ptr, d_child_list, d_batches, d_ld;
+    DevBuf<SolveDesc> d_sdesc;          // one packed descriptor per batch entry (same indexing as d_batches)
     DevBuf<int64_t> d_rows_ptr, d_panel_off, d_upd_off, d_woff, d_front_ptr, d_asm_base;
     DevBuf<int32_t> d_asm_colptr, d_asm_src, d_asm_child;
     // numeric
     DevBuf<double> d_L, d_U, d_W, d_D, d_Dinv, d_uvec, d_partial;
     DevBuf<double> d_b, d_x, d_e, d_dx, d_y, d_rx, d_rz;
     DevBuf<double> d_eps; DevBuf<unsigned long long> d_scal;   // [0] max|diag|, [1] normb, [2] norme
-    DevBuf<unsigned int> d_nreg;
+    DevBuf<unsigned int> d_nreg; DevBuf<int32_t> d_reglog;
     std::vector<LevelPlan> plan;
     std::vector<int32_t> h_batches;
     bool have_diag = false;
@@ -230,6 +232,7 @@ struct cb200_handle {
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool multi_stream = true;
+    bool sort_batches = true;          // CB200_SORT_BATCHES=0: keep the size order of the level lists
     // bottom subtrees of narrow supernodes solved by one CTA each (k_fwd_subtree / k_bwd_subtree)
     bool use_subtree = false;          // CB200_SUBTREE=1 turns them on.  Measured (C5): 5.58 ms per solve against 3.19 ms
                                        // level-scheduled - with only L streamed from HBM but metadata still fetched per
@@ -294,7 +297,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
     // classes of a level are independent: leaf + tiny on side[0], warp on side[1], CTA on side[2], big on the
     // main stream (fork/join only when a second class has work)
     const bool big_work = P.solve[3].cnt || P.tops.cnt;
-    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
+    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0 || P.solve[5].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
     const bool ms = h->ms_on() && nclass > 1;
     cudaStream_t s_leaf = ms ? h->side[0] : h->stream, s_warp = ms ? h->side[1] : h->stream,
                  s_cta = ms ? h->side[2] : h->stream;
@@ -307,21 +310,19 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
         LAUNCH(h);
         }
     }
-    const Batch& b4 = P.solve[4];
-    if (b4.cnt) {
-        { FineScope fs(h, Timers::F_FWD_SUB);
-        k_fwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, s_leaf>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
-                                                                   h->d_y.p, h->d_uvec.p);
-        LAUNCH(h);
-        }
-    }
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
-        { FineScope fs(h, Timers::F_FWD_WARP);
-        k_fwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), s_warp>>>(
-            ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
+        FineScope fs(h, Timers::F_FWD_WARP);
+        k_fwd_warp<32><<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * b1.maxnf * sizeof(double), s_warp>>>(
+            ds, h->d_sdesc.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
         LAUNCH(h);
-        }
+    }
+    const Batch& b5 = P.solve[5];
+    if (b5.cnt) {
+        FineScope fs(h, Timers::F_FWD_WARP);
+        k_fwd_warp<16><<<nblk(b5.cnt, WPB), WPB * 32, (size_t)WPB * b5.maxnf * sizeof(double), s_warp>>>(
+            ds, h->d_sdesc.p + b5.off, b5.cnt, b5.maxnf, h->d_L.p, h->d_y.p, h->d_uvec.p);
+        LAUNCH(h);
     }
     const Batch& b2 = P.solve[2];
     if (b2.cnt) {
@@ -378,7 +379,7 @@ void launch_fwd_level(cb200_handle* h, const LevelPlan& P, int lv) {
 void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     DevSym ds = devsym(h);
     const bool big_work = P.solve[3].cnt || P.tops.cnt;
-    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
+    const int nclass = (P.solve[0].cnt || P.solve[4].cnt) + (P.solve[1].cnt != 0 || P.solve[5].cnt != 0) + (P.solve[2].cnt != 0) + big_work;
     const bool ms = h->ms_on() && nclass > 1;
     cudaStream_t s_leaf = ms ? h->side[0] : h->stream, s_warp = ms ? h->side[1] : h->stream,
                  s_cta = ms ? h->side[2] : h->stream;
@@ -413,19 +414,17 @@ void launch_bwd_level(cb200_handle* h, const LevelPlan& P) {
     }
     const Batch& b1 = P.solve[1];
     if (b1.cnt) {
-        { FineScope fs(h, Timers::F_BWD_WARP);
-        k_bwd_warp<<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * (b1.maxnf + 32 + 32 * BT_LD) * sizeof(double), s_warp>>>(
-            ds, h->d_batches.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
+        FineScope fs(h, Timers::F_BWD_WARP);
+        k_bwd_warp<32><<<nblk(b1.cnt, WPB), WPB * 32, (size_t)WPB * (b1.maxnf + 32 + 32 * BT_LD) * sizeof(double), s_warp>>>(
+            ds, h->d_sdesc.p + b1.off, b1.cnt, b1.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
-        }
     }
-    const Batch& b4 = P.solve[4];
-    if (b4.cnt) {
-        { FineScope fs(h, Timers::F_BWD_SUB);
-        k_bwd_sub<<<nblk(b4.cnt, 256 / SG), 256, 0, s_leaf>>>(ds, h->d_batches.p + b4.off, b4.cnt, h->d_L.p,
-                                                                   h->d_Dinv.p, h->d_y.p);
+    const Batch& b5 = P.solve[5];
+    if (b5.cnt) {
+        FineScope fs(h, Timers::F_BWD_WARP);
+        k_bwd_warp<16><<<nblk(b5.cnt, WPB), WPB * 32, (size_t)WPB * (b5.maxnf + 32 + 32 * 17) * sizeof(double), s_warp>>>(
+            ds, h->d_sdesc.p + b5.off, b5.cnt, b5.maxnf, h->d_L.p, h->d_Dinv.p, h->d_y.p);
         LAUNCH(h);
-        }
     }
     const Batch& b0 = P.solve[0];
     if (b0.cnt) {
@@ -514,6 +513,11 @@ int build_plans(cb200_handle* h) {
         if (large) {
             std::stable_sort(v.begin(), v.end(), [&](int32_t x, int32_t y) { return S.ns(x) > S.ns(y); });
             for (int32_t sn : v) b.ns_desc.push_back(S.ns(sn));
+        } else if (h->sort_batches) {
+            // memory order: panels, update blocks and solution slices of consecutive supernodes are
+            // adjacent in HBM (postorder layout), so neighbouring warps / CTAs touch neighbouring DRAM
+            // pages instead of random ones (the level lists come sorted by front size)
+            std::sort(v.begin(), v.end());
         }
         b.off = (int32_t)batches.size(); b.cnt = (int32_t)v.size();
         int64_t w = 0;
@@ -601,8 +605,9 @@ int build_plans(cb200_handle* h) {
             } else cls[c].push_back(sn);
             const bool leaf = (S.ns(sn) == 1 && S.child_ptr[sn + 1] == S.child_ptr[sn]);
             const bool big = (int64_t)nf * S.ns(sn) >= 65536 && S.ns(sn) > 32;
-            const bool tiny = S.ns(sn) <= SG && nf <= 32;
-            const int d = leaf ? 0 : (tiny ? 4 : ((S.ns(sn) <= 32 && nf <= 192) ? 1 : (big ? 3 : 2)));
+            // (the 8-lane kernels for tiny supernodes are gone: the 16-column warp kernel takes them)
+            static const bool warp16 = !(getenv("CB200_WARP16") && getenv("CB200_WARP16")[0] == '0');    // debugging aid
+            const int d = leaf ? 0 : ((S.ns(sn) <= 32 && nf <= 192) ? (S.ns(sn) <= 16 && warp16 ? 5 : 1) : (big ? 3 : 2));
             if (!in_sub[sn]) scl[d].push_back(sn);
         }
         LevelPlan& P = h->plan[lv];
@@ -616,6 +621,19 @@ int build_plans(cb200_handle* h) {
     }
     h->h_batches = batches;
     CUDA_OK(h->d_batches.upload(batches, s)); CUDA_OK(h->d_woff.upload(woff, s));
+    {
+        std::vector<SolveDesc> sd(batches.size());
+        for (size_t i = 0; i < batches.size(); ++i) {
+            const int32_t sn = batches[i];
+            SolveDesc& d = sd[i];
+            d.f = S.sn_first[sn]; d.ns = S.ns(sn); d.nr = S.nr(sn); d.ld = S.panel_ld[sn];
+            d.nchild = S.child_ptr[sn + 1] - S.child_ptr[sn]; d.pad = 0; d.pad2 = 0;
+            d.panel_off = S.panel_off[sn]; d.rows_ptr = S.rows_ptr[sn]; d.front_ptr = S.front_ptr[sn]; d.asm_base = S.asm_base[sn];
+        }
+        CUDA_OK(h->d_sdesc.alloc(std::max<size_t>(1, sd.size())));
+        if (!sd.empty()) CUDA_OK(cudaMemcpyAsync(h->d_sdesc.p, sd.data(), sd.size() * sizeof(SolveDesc), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+    }
     CUDA_OK(h->d_W.alloc((size_t)std::max<int64_t>(1, wmax)));
     size_t pmax = 1;
     for (const LevelPlan& P : h->plan)
@@ -699,7 +717,7 @@ int factor_body(cb200_handle* h, bool static_reg) {
         h->tm.nlaunch += 3;
     }
     RegParams rp{h->st.dynamic_regularization_eps, h->st.dynamic_regularization_delta,
-                 h->st.dynamic_regularization_enable};
+                 h->st.dynamic_regularization_enable, h->d_reglog.p};
     DevSym ds = devsym(h);
     if (h->dist && h->rank != 0 && !h->h_top_list.empty()) {
         // the original entries of the replicated top fronts are contributed by rank 0 only
@@ -990,6 +1008,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         }
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         if (const char* e = getenv("CB200_MULTISTREAM")) h->multi_stream = e[0] != '0';
+        if (const char* e = getenv("CB200_SORT_BATCHES")) h->sort_batches = e[0] != '0';
         if (const char* e = getenv("CB200_SUBTREE")) h->use_subtree = e[0] == '1';
         cudaStream_t s = h->stream;
         // ---- K
@@ -1051,7 +1070,7 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
             CUDA_OK(b->alloc(std::max<int64_t>(1, N)));
             CUDA_OK(cudaMemsetAsync(b->p, 0, std::max<int64_t>(1, N) * sizeof(double), s));
         }
-        CUDA_OK(h->d_eps.alloc(1)); CUDA_OK(h->d_scal.alloc(4)); CUDA_OK(h->d_nreg.alloc(1));
+        CUDA_OK(h->d_eps.alloc(1)); CUDA_OK(h->d_scal.alloc(4)); CUDA_OK(h->d_nreg.alloc(1)); CUDA_OK(h->d_reglog.alloc(64));
         CUDA_OK(cudaMemsetAsync(h->d_eps.p, 0, sizeof(double), s));
         CUDA_OK(cudaMemsetAsync(h->d_nreg.p, 0, sizeof(unsigned int), s));
         // opt in to large dynamic shared memory for the bigger small-front classes
@@ -1069,7 +1088,8 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         { int rct = build_tensor_maps(h); if (rct) return rct; }
         CUDA_OK(cudaFuncSetAttribute(k_fwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        CUDA_OK(cudaFuncSetAttribute(k_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd_warp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(k_bwd_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (S.max_front > 25000) { set_error("front too large for the single-CTA solve kernels"); return -4; }
@@ -1454,6 +1474,13 @@ int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len) 
                   CUDA_OK(cudaMemcpyAsync(&v, h->d_nreg.p, sizeof(v), cudaMemcpyDeviceToHost, st));
                   CUDA_OK(cudaStreamSynchronize(st)); out[0] = (double)v; return 0; }
         case 6: src = h->d_x.p; n = h->N; break;       // full solution [x; z; expansion variables] of the last solve
+        case 7: { if (len != 64) { set_error("download: length"); return -2; }     // ORIGINAL indices of the first 64 regularised pivots
+                  int32_t v[64]; unsigned int cnt = 0;
+                  CUDA_OK(cudaMemcpyAsync(v, h->d_reglog.p, sizeof(v), cudaMemcpyDeviceToHost, st));
+                  CUDA_OK(cudaMemcpyAsync(&cnt, h->d_nreg.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+                  CUDA_OK(cudaStreamSynchronize(st));
+                  for (int i = 0; i < 64; ++i) out[i] = i < (int)cnt ? (double)h->S.perm[v[i]] : -1.0;
+                  return 0; }
         default: set_error("download: bad selector"); return -2;
     }
     if (len != n) { set_error("download: length mismatch"); return -2; }

@@ -8,7 +8,7 @@
 //   G5  large-front blocked LDL'          k_piv_diag, k_piv_rows, k_ldl_update_tma (TMA-fed 128 x 128 DMMA GEMM),
 //                                         k_ldl_update_ldg (fallback), k_finish_large
 //   G6  extend-add                        fused in G4 ; k_assemble_large ; k_assemble_atomic
-//   G7  multifrontal triangular solves    k_fwd_{leaf,sub,warp,cta}, k_bwd_*, k_big_{asm,tri,gemv}_*,
+//   G7  multifrontal triangular solves    k_fwd_{leaf,warp<16|32>,cta}, k_bwd_*, k_big_{asm,tri,gemv}_*, k_*_subtree,
 //                                         k_pack_perm, k_unpack_perm
 //   G8  symmetric SpMV residual + norm    k_residual, k_residual_long
 //   G9  multi-GPU helpers                 k_zero_panels, k_mask_vec  (collectives: api_cuda.cu)
@@ -39,7 +39,11 @@ struct DevSym {                 // device copies of the Symbolic arrays
                                 // assembles into the replicated top fronts (nullptr = all)
 };
 
-struct RegParams { double eps, delta; int enable; };
+struct RegParams { double eps, delta; int enable; int32_t* log; };   // log: first 64 regularised pivots (permuted column, unregularised value bits elsewhere)
+__device__ __forceinline__ void note_reg(const RegParams& rp, unsigned int* nreg, int col, unsigned int count = 1u) {
+    const unsigned int slot = atomicAdd(nreg, count);
+    if (rp.log && slot < 64u) rp.log[slot] = col;
+}
 constexpr int MANY_CHILDREN = 2048;   // fronts with more children are assembled by k_assemble_atomic
 
 
@@ -133,7 +137,7 @@ k_factor_small(DevSym S, const int32_t* __restrict__ batch, double* __restrict__
         for (int i = k + 1 + tid; i < nf; i += THREADS) F[i + k * nf] *= dinv;
         if (tid == 0) {
             F[k + k * nf] = d; D[f + k] = d; Dinv[f + k] = dinv;
-            if (reg) atomicAdd(nreg, 1u);
+            if (reg) note_reg(rp, nreg, f + k);
         }
         __syncthreads();
     }
@@ -174,6 +178,7 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
                double* __restrict__ Dinv, RegParams rp, unsigned int* __restrict__ nreg) {
     extern __shared__ double smem[];
     __shared__ double dvs[160], dis[160];
+    __shared__ double ps4[256];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -220,33 +225,23 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
     for (int kb = 0; kb < ns; kb += 16) {
         const int cbk = min(16, ns - kb);
         if (wid == 0) {
-            const int i = lane & 15;
-            double a[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                a[j] = (i < cbk && j <= i) ? P[(kb + i) + (kb + j) * nf] : ((i >= cbk && j == i) ? 1.0 : 0.0);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                double d = __shfl_sync(0xffffffffu, a[k], k);
+            // right-looking LDL' of the cbk x cbk diagonal sub-block in shared memory, lane j owns column
+            // kb + j.  (The former register/shuffle version sat inside a loop whose bounds the compiler cannot
+            // prove warp-uniform: every shuffle became a WARPSYNC.COLLECTIVE, ~50 cycles each.)
+            for (int k = 0; k < cbk; ++k) {
+                double d = P[(kb + k) + (kb + k) * nf];
+                const double sg = (double)S.dsign[f + kb + k];
                 bool reg = false;
-                if (k < cbk) {
-                    const double sg = (double)S.dsign[f + kb + k];
-                    if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
-                }
+                if (rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
                 const double dinv = 1.0 / d;
-                const double lik = a[k] * dinv;
-#pragma unroll
-                for (int j = k + 1; j < 16; ++j) {
-                    const double ajk = __shfl_sync(0xffffffffu, a[k], j);
-                    if (i >= j) a[j] -= lik * ajk;
+                if (lane > k && lane < cbk) {
+                    const double wj = P[(kb + lane) + (kb + k) * nf] * dinv;
+                    for (int i = lane; i < cbk; ++i) P[(kb + i) + (kb + lane) * nf] -= P[(kb + i) + (kb + k) * nf] * wj;
                 }
-                if (i > k) a[k] = lik;
-                if (i == k) a[k] = d;
-                if (lane == 0 && k < cbk) { dvs[kb + k] = d; dis[kb + k] = dinv; if (reg) atomicAdd(nreg, 1u); }
-            }
-            if (lane < 16 && i < cbk) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (j <= i) P[(kb + i) + (kb + j) * nf] = a[j];
+                __syncwarp();
+                if (lane > k && lane < cbk) P[(kb + lane) + (kb + k) * nf] *= dinv;
+                if (lane == 0) { P[(kb + k) + (kb + k) * nf] = d; dvs[kb + k] = d; dis[kb + k] = dinv; if (reg) note_reg(rp, nreg, f + kb + k); }
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -340,8 +335,9 @@ k_factor_panel(DevSym S, const int32_t* __restrict__ batch, int maxpanel, int ma
             double acc2 = 0.0;
             if (i > j && i < sb)
                 for (int k = j + 1 + part; k < i; k += 4) acc2 += P[(b0 + i) + (b0 + k) * nf] * P[(b0 + j) + (b0 + k) * nf];
-            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
-            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+            ps4[tid] = acc2;                         // 4 partial sums per column, summed through shared memory
+            __syncwarp();                            // (no shuffles inside this loop: see the note above)
+            if (part == 0) acc2 = (ps4[tid] + ps4[tid + 1]) + (ps4[tid + 2] + ps4[tid + 3]);
             if (part == 0 && i > j && i < sb) P[(b0 + j) + (b0 + i) * nf] = -(P[(b0 + i) + (b0 + j) * nf] + acc2);
             __syncwarp();
         }
@@ -833,7 +829,7 @@ k_piv_diag(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __
             bool reg = false;
             if (k < nb && rp.enable && d * sg < rp.eps) { d = rp.delta * sg; reg = true; }
             const double dinv = 1.0 / d;
-            if (tid == 0) { if (k < nb) { D[f + J0 + k] = d; Dinv[f + J0 + k] = dinv; } if (reg) ++myreg; }
+            if (tid == 0) { if (k < nb) { D[f + J0 + k] = d; Dinv[f + J0 + k] = dinv; } if (reg) { ++myreg; note_reg(rp, nreg, f + J0 + k); } }
             double li[4], cj[4], xr[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) { const int i = 4 * tx + r; li[r] = (i > k) ? cb[i] * dinv : 0.0; }
@@ -849,7 +845,7 @@ k_piv_diag(DevSym S, const int32_t* __restrict__ batch, int J0, const double* __
             }
         }
     }
-    if (tid == 0 && myreg) atomicAdd(nreg, myreg);
+    (void)myreg;
     // park [inv(L_JJ) strictly lower ; d on the diagonal] (column-major 64 x 64)
     double* Wd = Wst + woff[blockIdx.x] + (int64_t)(J0 / PB) * (PB * PB);
 #pragma unroll
@@ -1048,9 +1044,27 @@ __device__ __forceinline__ double row_dot64(const double* __restrict__ rowp, int
 
 // Transposed products for 8 consecutive columns at once: out[u] = sum_{r=r0+lane,+32,..<r1} col_u[r]*w[r]
 // (warp-level; result valid on all lanes after the shuffles)
-__device__ __forceinline__ void cols8_dot(const double* __restrict__ base, int64_t ld, int ncol,
-                                          int r0, int r1, const double* __restrict__ w, int lane,
-                                          double out[8]) {
+// Sum 8 per-lane partial sums over the warp through shared memory: lane u (< 8) returns sum_u.
+// (Shuffle trees inside loops whose trip count comes from memory are wrapped in WARPSYNC.COLLECTIVE
+// on sm_100a; `red` is 8 x 33 doubles owned by the warp.)
+__device__ __forceinline__ double warp_sum8_smem(const double (&a)[8], double* red, int lane) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) red[u * 33 + lane] = a[u];
+    __syncwarp();
+    double s = 0.0;
+    if (lane < 8) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) s += red[lane * 33 + l];
+    }
+    __syncwarp();
+    return s;
+}
+
+// Transposed products for 8 consecutive columns at once: sum_{r=r0+lane,+32,..<r1} col_u[r]*w[r];
+// lane u (< 8) returns the sum of column u.
+__device__ __forceinline__ double cols8_dot(const double* __restrict__ base, int64_t ld, int ncol,
+                                            int r0, int r1, const double* __restrict__ w, int lane,
+                                            double* red) {
     double a[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) a[u] = 0.0;
@@ -1066,12 +1080,7 @@ __device__ __forceinline__ void cols8_dot(const double* __restrict__ base, int64
 #pragma unroll
         for (int u = 0; u < 8; ++u) a[u] += v0[u] * w0 + v1[u] * w1;
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        double v = a[u];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        out[u] = v;
-    }
+    return warp_sum8_smem(a, red, lane);
 }
 
 // --- supernodes with a single pivot column and a short front: one thread per supernode
@@ -1137,74 +1146,93 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&p)[32], int lan
     return p[0];
 }
 
-// Forward step of one narrow supernode by one warp.  Y / U are the solution / contribution vectors
-// addressed with GLOBAL indices: in the level-scheduled kernels they are the global arrays, in the
-// subtree kernels they are shared-memory windows shifted by the window origin.
-__device__ __forceinline__ void fwd_warp_body(const DevSym& S, int s, const double* __restrict__ Lst,
-                                              double* Y, double* U, double* w, int lane) {
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    const int ld = S.ld[s];
-    const double* Lp = Lst + S.panel_off[s];
+// Everything a narrow-supernode solve step needs to know about its supernode, packed so that the
+// level-scheduled kernels fetch it with ONE round trip (batch position -> descriptor) instead of two
+// (batch position -> supernode id -> seven separate arrays).  64 bytes, built per batch entry.
+struct SolveDesc {
+    int32_t f, ns, nr, ld;
+    int32_t nchild, pad;
+    int64_t panel_off, rows_ptr, front_ptr, asm_base;
+    int64_t pad2;
+};
+struct SnView {                 // the same data as raw pointers
+    int f, ns, nr, ld; bool has_children;
+    const double* Lp; int64_t rp; const int32_t* cp; const int32_t* asrc; const int32_t* rows;
+};
+__device__ __forceinline__ SnView view_of(const DevSym& S, const SolveDesc& d, const double* Lst) {
+    SnView v; v.f = d.f; v.ns = d.ns; v.nr = d.nr; v.ld = d.ld; v.has_children = d.nchild != 0;
+    v.Lp = Lst + d.panel_off; v.rp = d.rows_ptr; v.cp = S.asm_colptr + d.front_ptr; v.asrc = S.asm_src + d.asm_base;
+    v.rows = S.rows + d.rows_ptr;
+    return v;
+}
+__device__ __forceinline__ SnView view_of(const DevSym& S, int s, const double* Lst) {
+    SnView v; v.f = S.sn_first[s]; v.ns = S.sn_first[s + 1] - v.f; v.rp = S.rows_ptr[s];
+    v.nr = (int)(S.rows_ptr[s + 1] - v.rp); v.ld = S.ld[s]; v.has_children = S.child_ptr[s + 1] != S.child_ptr[s];
+    v.Lp = Lst + S.panel_off[s]; v.cp = S.asm_colptr + S.front_ptr[s]; v.asrc = S.asm_src + S.asm_base[s];
+    v.rows = S.rows + v.rp;
+    return v;
+}
+
+// Forward step of one narrow supernode (ns <= NW) by one warp.  Y / U are the solution / contribution
+// vectors addressed with GLOBAL indices: in the level-scheduled kernels they are the global arrays, in
+// the subtree kernels they are shared-memory windows shifted by the window origin.
+template <int NW>
+__device__ __forceinline__ void fwd_warp_body(const SnView& V, double* Y, double* U, double* w, int lane) {
+    const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
+    const double* Lp = V.Lp;
     // the triangle loads do not depend on the gathered right-hand side: issue them first
-    double v[32];
+    double v[NW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
-    {
-        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
-        const int64_t base = S.asm_base[s];
+    for (int j = 0; j < NW; ++j) v[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    if (V.has_children) {
         for (int i = lane; i < nf; i += 32) {
             double acc = i < ns ? Y[f + i] : 0.0;
-            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += U[S.asm_src[base + e]];
+            for (int e = V.cp[i]; e < V.cp[i + 1]; ++e) acc += U[V.asrc[e]];
             w[i] = acc;
         }
+    } else {
+        for (int i = lane; i < nf; i += 32) w[i] = i < ns ? Y[f + i] : 0.0;
     }
     __syncwarp();
     // x = inv(L11) w_top : x_i = w_i + sum_{j<i} X[i][j] w_j
     double xi = (lane < ns) ? w[lane] : 0.0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < ns) xi += v[j] * w[j];
+    for (int j = 0; j < NW; ++j) if (j < ns) xi += v[j] * w[j];
     __syncwarp();
     if (lane < ns) { w[lane] = xi; Y[f + lane] = xi; }
     __syncwarp();
     // u = w_bot - L21 x : one row per lane, all ns column loads of a row in flight together
     for (int r = ns + lane; r < nf; r += 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
+        for (int j = 0; j < NW; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
-        U[rp + r - ns] = w[r] - (a0 + a1);
+        for (int j = 0; j < NW; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
+        U[V.rp + r - ns] = w[r] - (a0 + a1);
     }
 }
 
 // Backward step of one narrow supernode by one warp.  Columns in [win_lo, win_hi) are read from the
 // window Y, all others (ancestors outside a subtree) from the global solution vector yg.
-// The transposed products go through a 32 x 33 shared tile (coalesced loads by rows, conflict-free
+// The transposed products go through a 32 x (NW+1) shared tile (coalesced loads by rows, conflict-free
 // reads by columns) instead of shuffle reductions: inside the loops of the subtree kernel the compiler
 // cannot prove warp convergence and wraps every shuffle in WARPSYNC.COLLECTIVE (~50 cycles each).
 constexpr int BT_LD = 33;
-__device__ __forceinline__ void bwd_warp_body(const DevSym& S, int s, const double* __restrict__ Lst,
-                                              const double* __restrict__ Dinv, double* Y, const double* yg,
-                                              int win_lo, int win_hi, double* w, double* tile, int lane) {
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    const int ld = S.ld[s];
-    const double* Lp = Lst + S.panel_off[s];
+template <int NW>
+__device__ __forceinline__ void bwd_warp_body(const SnView& V, const double* __restrict__ Dinv, double* Y,
+                                              const double* yg, int win_lo, int win_hi, double* w,
+                                              double* tile, int lane) {
+    const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
+    const double* Lp = V.Lp;
+    constexpr int TL = NW + 1;
     // the triangle (row `lane`): X[lane][j], j < lane - independent of the gather below
-    double xr[32];
+    double xr[NW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) xr[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    for (int j = 0; j < NW; ++j) xr[j] = (j < lane && lane < ns) ? Lp[(int64_t)j * ld + lane] : 0.0;
     for (int i = lane; i < nf; i += 32) {
         double val;
         if (i < ns) val = Y[f + i] * Dinv[f + i];
-        else { const int c = S.rows[rp + i - ns]; val = (c >= win_lo && c < win_hi) ? Y[c] : yg[c]; }
+        else { const int c = V.rows[i - ns]; val = (c >= win_lo && c < win_hi) ? Y[c] : yg[c]; }
         w[i] = val;
     }
     __syncwarp();
@@ -1212,49 +1240,57 @@ __device__ __forceinline__ void bwd_warp_body(const DevSym& S, int s, const doub
     double acc = 0.0;
     for (int r0 = ns; r0 < nf; r0 += 32) {
         const int r = r0 + lane;
-        double v[32];
+        double v[NW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (j < ns && r < nf) ? Lp[(int64_t)j * ld + r] : 0.0;
+        for (int j = 0; j < NW; ++j) v[j] = (j < ns && r < nf) ? Lp[(int64_t)j * ld + r] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tile[lane * BT_LD + j] = v[j];
+        for (int j = 0; j < NW; ++j) tile[lane * TL + j] = v[j];
         __syncwarp();
+        if (lane < NW) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) { const double wr = (r0 + rr < nf) ? w[r0 + rr] : 0.0; acc += tile[rr * BT_LD + lane] * wr; }
+            for (int rr = 0; rr < 32; ++rr) { const double wr = (r0 + rr < nf) ? w[r0 + rr] : 0.0; acc += tile[rr * TL + lane] * wr; }
+        }
         __syncwarp();
     }
     const double tj = (lane < ns) ? w[lane] - acc : 0.0;
     // x_j = t_j + sum_{i>j} X[i][j] t_i
 #pragma unroll
-    for (int j = 0; j < 32; ++j) tile[lane * BT_LD + j] = xr[j];
+    for (int j = 0; j < NW; ++j) tile[lane * TL + j] = xr[j];
     __syncwarp();                                  // everyone has read w[0..ns) above
-    if (lane < 32) w[lane] = tj;                   // t (zero beyond ns)
+    w[lane] = tj;                                  // t (zero beyond ns)
     __syncwarp();
     double corr = 0.0;
+    if (lane < NW) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) corr += tile[i * BT_LD + lane] * w[i];
+        for (int i = 0; i < NW; ++i) corr += tile[i * TL + lane] * w[i];
+    }
     if (lane < ns) Y[f + lane] = tj + corr;
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(WPB * 32, 2)
-k_fwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
+template <int NW>
+__global__ void __launch_bounds__(WPB * 32, NW == 16 ? 4 : 2)
+k_fwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
            const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int idx = blockIdx.x * WPB + wid;
     if (idx >= count) return;
-    fwd_warp_body(S, batch[idx], Lst, y, uvec, smem + (size_t)wid * maxnf, lane);
+    const SolveDesc d = desc[idx];
+    fwd_warp_body<NW>(view_of(S, d, Lst), y, uvec, smem + (size_t)wid * maxnf, lane);
 }
 
-__global__ void __launch_bounds__(WPB * 32, 2)
-k_bwd_warp(DevSym S, const int32_t* __restrict__ batch, int count, int maxnf,
+template <int NW>
+__global__ void __launch_bounds__(WPB * 32, NW == 16 ? 4 : 2)
+k_bwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
            const double* __restrict__ Lst, const double* __restrict__ Dinv, double* __restrict__ y) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int idx = blockIdx.x * WPB + wid;
     if (idx >= count) return;
-    double* base = smem + (size_t)wid * (maxnf + 32 + 32 * BT_LD);       // w (padded to >= 32) then the tile
-    bwd_warp_body(S, batch[idx], Lst, Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
+    const SolveDesc d = desc[idx];
+    double* base = smem + (size_t)wid * (maxnf + 32 + 32 * (NW + 1));    // w (padded to >= 32) then the tile
+    bwd_warp_body<NW>(view_of(S, d, Lst), Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
 }
 
 // --- whole subtrees of narrow supernodes: one CTA per subtree, no level barrier across the grid.
@@ -1297,7 +1333,7 @@ k_fwd_subtree(DevSym S, SubTrees T, const double* __restrict__ Lst, double* __re
     for (int l = 0; l < T.nlev; ++l) {
         const int e0 = lo[l], e1 = lo[l + 1];
         if (e0 == e1) continue;                                // (uniform) nothing on this level
-        for (int k = e0 + wid; k < e1; k += 8) fwd_warp_body(S, ord[k], Lst, Y, U, w, lane);
+        for (int k = e0 + wid; k < e1; k += 8) fwd_warp_body<32>(view_of(S, ord[k], Lst), Y, U, w, lane);
         __syncthreads();
     }
     for (int i = tid; i < col_hi - col_lo; i += 256) y[col_lo + i] = ysm[i];
@@ -1326,89 +1362,10 @@ k_bwd_subtree(DevSym S, SubTrees T, const double* __restrict__ Lst, const double
     for (int l = T.nlev - 1; l >= 0; --l) {
         const int e0 = lo[l], e1 = lo[l + 1];
         if (e0 == e1) continue;
-        for (int k = e0 + wid; k < e1; k += 8) bwd_warp_body(S, ord[k], Lst, Dinv, Y, y, col_lo, col_hi, w, tile, lane);
+        for (int k = e0 + wid; k < e1; k += 8) bwd_warp_body<32>(view_of(S, ord[k], Lst), Dinv, Y, y, col_lo, col_hi, w, tile, lane);
         __syncthreads();
     }
     for (int i = tid; i < col_hi - col_lo; i += 256) y[col_lo + i] = ysm[i];
-}
-
-// --- tiny supernodes (ns <= 8, nf <= 32, with children): 8 lanes per supernode, 32 supernodes
-// per CTA.  Groups of one warp diverge freely: every shuffle / sync uses the group's own mask.
-constexpr int SG = 8;
-__global__ void __launch_bounds__(256)
-k_fwd_sub(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
-          double* __restrict__ y, double* __restrict__ uvec) {
-    __shared__ double smem[256 / SG][32];
-    const int g = threadIdx.x / SG, sub = threadIdx.x % SG;
-    const int idx = blockIdx.x * (256 / SG) + g;
-    if (idx >= count) return;
-    const unsigned mask = ((1u << SG) - 1u) << (((threadIdx.x & 31) / SG) * SG);
-    double* w = smem[g];
-    const int s = batch[idx];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    {
-        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
-        const int64_t base = S.asm_base[s];
-        for (int i = sub; i < nf; i += SG) {
-            double acc = i < ns ? y[f + i] : 0.0;
-            for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
-            w[i] = acc;
-        }
-    }
-    __syncwarp(mask);
-    const double* Lp = Lst + S.panel_off[s];
-    double xi = 0.0;
-    if (sub < ns) {
-        xi = w[sub];
-        for (int j = 0; j < sub; ++j) xi += Lp[(int64_t)j * nf + sub] * w[j];
-    }
-    __syncwarp(mask);
-    if (sub < ns) { w[sub] = xi; y[f + sub] = xi; }
-    __syncwarp(mask);
-    for (int r = ns + sub; r < nf; r += SG) {
-        double acc = w[r];
-        for (int j = 0; j < ns; ++j) acc -= Lp[(int64_t)j * nf + r] * w[j];
-        uvec[rp + r - ns] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_bwd_sub(DevSym S, const int32_t* __restrict__ batch, int count, const double* __restrict__ Lst,
-          const double* __restrict__ Dinv, double* __restrict__ y) {
-    __shared__ double smem[256 / SG][32];
-    const int g = threadIdx.x / SG, sub = threadIdx.x % SG;
-    const int idx = blockIdx.x * (256 / SG) + g;
-    if (idx >= count) return;
-    const int gbase = ((threadIdx.x & 31) / SG) * SG;
-    const unsigned mask = ((1u << SG) - 1u) << gbase;
-    double* w = smem[g];
-    const int s = batch[idx];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    for (int i = sub; i < nf; i += SG) w[i] = i < ns ? y[f + i] * Dinv[f + i] : y[S.rows[rp + i - ns]];
-    __syncwarp(mask);
-    const double* Lp = Lst + S.panel_off[s];
-    double tj = 0.0;
-    for (int j = 0; j < ns; ++j) {
-        const double* cj = Lp + (int64_t)j * nf;
-        double acc = 0.0;
-        for (int r = ns + sub; r < nf; r += SG) acc += cj[r] * w[r];
-        for (int o = SG / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(mask, acc, o);
-        if (sub == j) tj = w[j] - acc;
-    }
-    double xj = tj;
-    for (int i = 1; i < ns; ++i) {
-        const double ti = __shfl_sync(mask, tj, gbase + i);
-        if (sub < i) xj += Lp[(int64_t)sub * nf + i] * ti;
-    }
-    if (sub < ns) y[f + sub] = xj;
 }
 
 // --- wide supernodes: one CTA (256 threads) per supernode, blocked over SB pivot columns
@@ -1468,6 +1425,7 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
           const double* __restrict__ Dinv, double* __restrict__ y) {
     extern __shared__ double w[];
     __shared__ double ts[SB];
+    __shared__ double red8[8][8 * 33];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -1487,9 +1445,8 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         {   // warp `wid` owns columns 8*wid .. 8*wid+7 of the block
             const int j0 = wid * 8;
             if (j0 < sb) {
-                double o8[8];
-                cols8_dot(Lp + (int64_t)(kb + j0) * ld, ld, min(8, sb - j0), kb + sb, nf, w, lane, o8);
-                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kb + j0 + lane] - o8[lane];
+                const double o = cols8_dot(Lp + (int64_t)(kb + j0) * ld, ld, min(8, sb - j0), kb + sb, nf, w, lane, red8[wid]);
+                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kb + j0 + lane] - o;
             }
         }
         __syncthreads();
@@ -1509,12 +1466,8 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
                     }
                     a[u] = v0 + v1;
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    double v = a[u];
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == u && j0 + u < sb) w[kb + j0 + u] = ts[j0 + u] + v;
-                }
+                const double v = warp_sum8_smem(a, red8[wid], lane);
+                if (lane < 8 && j0 + lane < sb) w[kb + j0 + lane] = ts[j0 + lane] + v;
             }
         }
         __syncthreads();
@@ -1610,6 +1563,14 @@ k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double*
     for (int kk = 0; kk < wp; kk += SB) {
         const int kb = kb0 + kk;
         const int sb = min(SB, wp - kk);
+        // the row of the panel below this block that the thread will update: its loads do not depend
+        // on x_kb, so they are issued BEFORE the block solve (one memory latency per block, not three)
+        const int r = kk + sb + tid;
+        const bool has_r = r < wp;
+        const double* rowp = Lp + (int64_t)kb * ld + kb0 + r;
+        double v[SB];
+#pragma unroll
+        for (int u = 0; u < SB; ++u) v[u] = (has_r && u < sb) ? rowp[(int64_t)u * ld] : 0.0;
         {
             const int i = tid & 63, qd = tid >> 6;
             double acc = 0.0;
@@ -1620,8 +1581,12 @@ k_big_tri_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double*
         if (tid < sb) xs[tid] = w[kk + tid] + part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
         __syncthreads();
         if (tid < sb) w[kk + tid] = xs[tid];
-        const double* blk = Lp + (int64_t)kb * ld + kb0;       // rows relative to panel start
-        for (int r = kk + sb + tid; r < wp; r += 256) w[r] -= row_dot64(blk + r, ld, sb, xs);
+        if (has_r) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < SB; u += 2) { a0 += v[u] * xs[u]; a1 += v[u + 1] * xs[u + 1]; }
+            w[r] -= a0 + a1;
+        }
         __syncthreads();
     }
     if (tid < wp) y[f + kb0 + tid] = w[tid];
@@ -1657,7 +1622,7 @@ k_big_gemv_fwd(DevSym S, const int32_t* __restrict__ batch, int pk, const double
         const int j0 = q * (WP / 4), j1 = min(wp, j0 + WP / 4);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int j = j0;
-        for (; j + 16 <= j1; j += 16) {
+        for (; j + 16 <= j1; j += 16) {        // (batches of 32 were measured slower: 246 registers)
             double v[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) v[u] = rowp[(int64_t)(j + u) * ld];
@@ -1685,6 +1650,7 @@ k_big_gemvT_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtile
                 const double* __restrict__ Lst, const double* __restrict__ y,
                 double* __restrict__ partial) {
     __shared__ double ws[BRT];
+    __shared__ double red4[8][4 * 33];
     const int s = batch[blockIdx.y];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -1709,12 +1675,17 @@ k_big_gemvT_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtile
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (j + u < wp) a[u] += Lp[(int64_t)(j + u) * ld + i] * wv;
         }
+        // cross-lane sums through shared memory (shuffles in this loop would be WARPSYNC.COLLECTIVE'd)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double v = a[u];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && j + u < wp) out[j + u] = v;
+        for (int u = 0; u < 4; ++u) red4[wid][u * 33 + lane] = a[u];
+        __syncwarp();
+        if (lane < 4) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) v += red4[wid][lane * 33 + l];
+            if (j + lane < wp) out[j + lane] = v;
         }
+        __syncwarp();
     }
 }
 
@@ -1725,6 +1696,7 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
               const double* __restrict__ partial, double* __restrict__ y) {
     __shared__ double w[WP];
     __shared__ double ts[SB];
+    __shared__ double red8[8][8 * 33];
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;
@@ -1751,9 +1723,8 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
         {
             const int j0 = wid * 8;
             if (j0 < sb) {
-                double o8[8];
-                cols8_dot(Lp + (int64_t)(kb + j0) * ld + kb0, ld, min(8, sb - j0), kk + sb, wp, w, lane, o8);
-                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kk + j0 + lane] - o8[lane];
+                const double o = cols8_dot(Lp + (int64_t)(kb + j0) * ld + kb0, ld, min(8, sb - j0), kk + sb, wp, w, lane, red8[wid]);
+                if (lane < 8 && j0 + lane < sb) ts[j0 + lane] = w[kk + j0 + lane] - o;
             }
         }
         __syncthreads();
@@ -1773,12 +1744,8 @@ k_big_tri_bwd(DevSym S, const int32_t* __restrict__ batch, int pk, int maxtiles,
                     }
                     a[u] = v0 + v1;
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    double v = a[u];
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == u && j0 + u < sb) w[kk + j0 + u] = ts[j0 + u] + v;
-                }
+                const double v = warp_sum8_smem(a, red8[wid], lane);
+                if (lane < 8 && j0 + lane < sb) w[kk + j0 + lane] = ts[j0 + lane] + v;
             }
         }
         __syncthreads();

@@ -144,7 +144,8 @@ int32_t cb200_update_A(cb200_handle* h, const double* values, int64_t len);
 /* ---------------------------------------------------------------- introspection (tests / bench)
  * what: 0 device KKT nzval (unregularised, len nnzK), 1 D (permuted, len N), 2 panel storage,
  *       3 perm (as doubles), 4 last static regulariser (len 1), 5 regularised-pivot count (len 1),
- *       6 full solution [x; z; expansion variables] of the last solve (len N) */
+ *       6 full solution [x; z; expansion variables] of the last solve (len N),
+ *       7 original indices of the first 64 dynamically regularised pivots of the last factorisation (len 64, -1 = none) */
 int32_t cb200_download(cb200_handle* h, int32_t what, double* out, int64_t len);
 /* timers (ms, accumulated CUDA-event times on the handle's stream): 0 cone update + scatter,
  * 1 factor, 2 triangular solves, 3 spmv/residual ; counters: 4 #factor, 5 #solves, 6 #kernel launches ;

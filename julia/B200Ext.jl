@@ -35,7 +35,8 @@ mutable struct B200DirectLDLSolver{T} <: AbstractDirectLDLSolver{T}
             settings.dynamic_regularization_eps, settings.dynamic_regularization_delta,
             settings.iterative_refinement_enable, settings.iterative_refinement_reltol,
             settings.iterative_refinement_abstol, settings.iterative_refinement_max_iter,
-            settings.iterative_refinement_stop_ratio, s.ordering, s.amd_dense_scale,
+            settings.iterative_refinement_stop_ratio, s.ordering,   # 1 = auto: the LIBRARY picks the PSD-safe order when
+            s.amd_dense_scale,                                       # K holds dense cone blocks (INTEGRATION.md section 5)
             s.nd_leaf_size, s.use_cuda_graph, s.reserved)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:cb200_create, LIB), Int32,
