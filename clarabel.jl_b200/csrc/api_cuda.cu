@@ -1103,6 +1103,10 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
 void cb200_destroy(cb200_handle* h) {
     if (!h) return;
     if (h->stream) { cudaStreamSynchronize(h->stream); }
+    // graphs captured with NCCL kernels inside hold references on the communicator: ncclCommDestroy waits
+    // for them, so the executables go first (seen as a teardown hang with CB200_DIST_GRAPH=1)
+    for (GraphExec* g : {&h->g_factor[0], &h->g_factor[1], &h->g_solve})
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
     if (h->comm && g_nccl.ok) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     cudaStream_t s = h->stream;
     for (int i = 0; i < 3; ++i) {

@@ -1396,6 +1396,14 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
     const double* Lp = Lst + S.panel_off[s];
     for (int kb = 0; kb < ns; kb += SB) {
         const int sb = min(SB, ns - kb);
+        const double* blk = Lp + (int64_t)kb * ld;
+        // the first row below the block this thread updates: its loads do not depend on x_kb and are
+        // issued BEFORE the block solve (one memory latency per block instead of three)
+        const int r1 = kb + sb + tid;
+        const bool has1 = r1 < nf;
+        double v[SB];
+#pragma unroll
+        for (int u = 0; u < SB; ++u) v[u] = (has1 && u < sb) ? blk[(int64_t)u * ld + r1] : 0.0;
         // diagonal block: x_i = w_i + sum_{j<i} Linv[i,j] w_j ; 4 threads per row split j
         {
             const int i = tid & 63, qd = tid >> 6;
@@ -1411,8 +1419,13 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         __syncthreads();
         if (tid < sb) w[kb + tid] = xs[tid];
         // rows below the block
-        const double* blk = Lp + (int64_t)kb * ld;
-        for (int r = kb + sb + tid; r < nf; r += 256) w[r] -= row_dot64(blk + r, ld, sb, xs);
+        if (has1) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < SB; u += 2) { if (u < sb) a0 += v[u] * xs[u]; if (u + 1 < sb) a1 += v[u + 1] * xs[u + 1]; }
+            w[r1] -= a0 + a1;
+        }
+        for (int r = r1 + 256; r < nf; r += 256) w[r] -= row_dot64(blk + r, ld, sb, xs);
         __syncthreads();
     }
     for (int i = tid; i < nf; i += 256) {
