@@ -688,7 +688,7 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
                 mbar_wait(empty + st, ph ^ 1u);                      // slot free (passes at once on a fresh barrier)
                 mbar_expect_tx(full + st, 2u * TTILE * (uint32_t)sizeof(double));
                 const int kc = u.k0 + it * TK;
-                if (kmajor) {
+                if (kmajor & 1) {
                     tma_load_3d(sA + st * TTILE, tm, full + st, 0, kc, u.ti * (T / 8));
                     tma_load_3d(sB + st * TTILE, tm, full + st, 0, kc, u.tj * (T / 8));
                 } else {
@@ -700,7 +700,7 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
         return;
     }
     // ===== 8 consumer warps (2 x 4), warp tile 64 x 32 = 4 x 4 DMMA m16n8k16 tiles per k-slab =====
-    const int sk = kmajor ? 8 : T, srg = kmajor ? TK * 8 : 8;       // strides (doubles) of k and of a row-group
+    const int sk = (kmajor & 1) ? 8 : T, srg = (kmajor & 1) ? TK * 8 : 8;       // strides (doubles) of k and of a row-group
     const int wm = (wid & 1) * WM, wn = (wid >> 1) * WN;
     const int g = lane >> 2, t = lane & 3;
     const double* Dv = D + f;
@@ -735,6 +735,7 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
 #pragma unroll
             for (int j = 0; j < NJ; ++j) dmma16816(acc[i][j], af, bf[j]);
         }
+        if (kmajor & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // debugging aid (CB200_TMA_FENCE)
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
     }
@@ -1180,6 +1181,122 @@ template <int NW>
 __device__ __forceinline__ void fwd_warp_body(const SnView& V, double* Y, double* U, double* w, int lane) {
     const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
     const double* Lp = V.Lp;
+    // Row `lane` of the first 32 panel rows, all of it in flight before anything else: for lane < ns that
+    // is the inverted triangle (columns j < lane), for ns <= lane < nf the first chunk of L21 (all ns
+    // columns).  Fronts with nf <= 32 - the bottom level, most of the bytes of this class - then need no
+    // further L round trip.  The loads do not depend on the gathered right-hand side.
+    double v[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) v[j] = (j < lane && j < ns && lane < nf) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    if (V.has_children) {
+        for (int i = lane; i < nf; i += 32) {
+            double acc = i < ns ? Y[f + i] : 0.0;
+            for (int e = V.cp[i]; e < V.cp[i + 1]; ++e) acc += U[V.asrc[e]];
+            w[i] = acc;
+        }
+    } else {
+        for (int i = lane; i < nf; i += 32) w[i] = i < ns ? Y[f + i] : 0.0;
+    }
+    __syncwarp();
+    // x = inv(L11) w_top : x_i = w_i + sum_{j<i} X[i][j] w_j
+    double xi = 0.0;
+    if (lane < ns) {
+        xi = w[lane];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) if (j < ns) xi += v[j] * w[j];
+    }
+    __syncwarp();
+    if (lane < ns) { w[lane] = xi; Y[f + lane] = xi; }
+    __syncwarp();
+    // u = w_bot - L21 x : rows ns..31 from the registers loaded above
+    if (lane >= ns && lane < nf) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
+        U[V.rp + lane - ns] = w[lane] - (a0 + a1);
+    }
+    // rows 32.. : one row per lane, all ns column loads of a row in flight together
+    for (int r = 32 + lane; r < nf; r += 32) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) v[j] = (j < ns) ? Lp[(int64_t)j * ld + r] : 0.0;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; j += 2) { if (j < ns) a0 += v[j] * w[j]; if (j + 1 < ns) a1 += v[j + 1] * w[j + 1]; }
+        U[V.rp + r - ns] = w[r] - (a0 + a1);
+    }
+}
+
+// Backward step of one narrow supernode by one warp.  Columns in [win_lo, win_hi) are read from the
+// window Y, all others (ancestors outside a subtree) from the global solution vector yg.
+// The transposed products go through a 32 x (NW+1) shared tile (coalesced loads by rows, conflict-free
+// reads by columns) instead of shuffle reductions: inside the loops of the subtree kernel the compiler
+// cannot prove warp convergence and wraps every shuffle in WARPSYNC.COLLECTIVE (~50 cycles each).
+constexpr int BT_LD = 33;
+template <int NW>
+__device__ __forceinline__ void bwd_warp_body(const SnView& V, const double* __restrict__ Dinv, double* Y,
+                                              const double* yg, int win_lo, int win_hi, double* w,
+                                              double* tile, int lane) {
+    const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
+    const double* Lp = V.Lp;
+    constexpr int TL = NW + 1;
+    // row `lane` of the first 32 panel rows (see fwd_warp_body): triangle X[lane][j], j < lane, for
+    // lane < ns; first chunk of L21 for ns <= lane < nf.  Independent of the gather below.
+    double xr[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) xr[j] = (j < lane && j < ns && lane < nf) ? Lp[(int64_t)j * ld + lane] : 0.0;
+    for (int i = lane; i < nf; i += 32) {
+        double val;
+        if (i < ns) val = Y[f + i] * Dinv[f + i];
+        else { const int c = V.rows[i - ns]; val = (c >= win_lo && c < win_hi) ? Y[c] : yg[c]; }
+        w[i] = val;
+    }
+#pragma unroll
+    for (int j = 0; j < NW; ++j) tile[lane * TL + j] = xr[j];
+    __syncwarp();
+    // t_j = w_j - sum_{r >= ns} L[r][j] w_r   (lane j owns column j); rows ns..31 sit in the tile already
+    double acc = 0.0;
+    if (lane < NW) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) if (rr >= ns && rr < nf) acc += tile[rr * TL + lane] * w[rr];
+    }
+    for (int r0 = 32; r0 < nf; r0 += 32) {
+        const int r = r0 + lane;
+        double v[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) v[j] = (j < ns && r < nf) ? Lp[(int64_t)j * ld + r] : 0.0;
+        __syncwarp();                              // the previous tile has been consumed
+#pragma unroll
+        for (int j = 0; j < NW; ++j) tile[lane * TL + j] = v[j];
+        __syncwarp();
+        if (lane < NW) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) if (r0 + rr < nf) acc += tile[rr * TL + lane] * w[r0 + rr];
+        }
+    }
+    const double tj = (lane < ns) ? w[lane] - acc : 0.0;
+    // x_j = t_j + sum_{i>j} X[i][j] t_i
+    __syncwarp();                                  // everyone has read w[0..nf) and the last tile
+    if (nf > 32) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) tile[lane * TL + j] = xr[j];
+    }
+    w[lane] = tj;                                  // t (zero beyond ns)
+    __syncwarp();
+    double corr = 0.0;
+    if (lane < NW) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) if (i < ns) corr += tile[i * TL + lane] * w[i];
+    }
+    if (lane < ns) Y[f + lane] = tj + corr;
+    __syncwarp();
+}
+
+// The previous formulation (triangle and L21 rows loaded in two separate phases): kept selectable
+// (CB200_SPLIT_ROWS=1) so that the merged-load bodies above can be measured against it on the same build.
+template <int NW>
+__device__ __forceinline__ void fwd_warp_body_split(const SnView& V, double* Y, double* U, double* w, int lane) {
+    const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
+    const double* Lp = V.Lp;
     // the triangle loads do not depend on the gathered right-hand side: issue them first
     double v[NW];
 #pragma unroll
@@ -1212,14 +1329,8 @@ __device__ __forceinline__ void fwd_warp_body(const SnView& V, double* Y, double
     }
 }
 
-// Backward step of one narrow supernode by one warp.  Columns in [win_lo, win_hi) are read from the
-// window Y, all others (ancestors outside a subtree) from the global solution vector yg.
-// The transposed products go through a 32 x (NW+1) shared tile (coalesced loads by rows, conflict-free
-// reads by columns) instead of shuffle reductions: inside the loops of the subtree kernel the compiler
-// cannot prove warp convergence and wraps every shuffle in WARPSYNC.COLLECTIVE (~50 cycles each).
-constexpr int BT_LD = 33;
 template <int NW>
-__device__ __forceinline__ void bwd_warp_body(const SnView& V, const double* __restrict__ Dinv, double* Y,
+__device__ __forceinline__ void bwd_warp_body_split(const SnView& V, const double* __restrict__ Dinv, double* Y,
                                               const double* yg, int win_lo, int win_hi, double* w,
                                               double* tile, int lane) {
     const int f = V.f, ns = V.ns, nf = V.ns + V.nr, ld = V.ld;
@@ -1268,8 +1379,8 @@ __device__ __forceinline__ void bwd_warp_body(const SnView& V, const double* __r
     __syncwarp();
 }
 
-template <int NW>
-__global__ void __launch_bounds__(WPB * 32, NW == 16 ? 4 : 2)
+template <int NW, bool MERGED>
+__global__ void __launch_bounds__(WPB * 32, NW == 16 ? (MERGED ? 3 : 4) : 2)
 k_fwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
            const double* __restrict__ Lst, double* __restrict__ y, double* __restrict__ uvec) {
     extern __shared__ double smem[];
@@ -1277,11 +1388,12 @@ k_fwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
     const int idx = blockIdx.x * WPB + wid;
     if (idx >= count) return;
     const SolveDesc d = desc[idx];
-    fwd_warp_body<NW>(view_of(S, d, Lst), y, uvec, smem + (size_t)wid * maxnf, lane);
+    if constexpr (MERGED) fwd_warp_body<NW>(view_of(S, d, Lst), y, uvec, smem + (size_t)wid * maxnf, lane);
+    else fwd_warp_body_split<NW>(view_of(S, d, Lst), y, uvec, smem + (size_t)wid * maxnf, lane);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(WPB * 32, NW == 16 ? 4 : 2)
+template <int NW, bool MERGED>
+__global__ void __launch_bounds__(WPB * 32, NW == 16 ? (MERGED ? 3 : 4) : 2)
 k_bwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
            const double* __restrict__ Lst, const double* __restrict__ Dinv, double* __restrict__ y) {
     extern __shared__ double smem[];
@@ -1290,7 +1402,8 @@ k_bwd_warp(DevSym S, const SolveDesc* __restrict__ desc, int count, int maxnf,
     if (idx >= count) return;
     const SolveDesc d = desc[idx];
     double* base = smem + (size_t)wid * (maxnf + 32 + 32 * (NW + 1));    // w (padded to >= 32) then the tile
-    bwd_warp_body<NW>(view_of(S, d, Lst), Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
+    if constexpr (MERGED) bwd_warp_body<NW>(view_of(S, d, Lst), Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
+    else bwd_warp_body_split<NW>(view_of(S, d, Lst), Dinv, y, y, 0, 0x7fffffff, base, base + maxnf + 32, lane);
 }
 
 // --- whole subtrees of narrow supernodes: one CTA per subtree, no level barrier across the grid.
@@ -1370,22 +1483,18 @@ k_bwd_subtree(DevSym S, SubTrees T, const double* __restrict__ Lst, const double
 
 // --- wide supernodes: one CTA (256 threads) per supernode, blocked over SB pivot columns
 __global__ void __launch_bounds__(256)
-k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict__ Lst,
+k_fwd_cta(DevSym S, const SolveDesc* __restrict__ desc, const double* __restrict__ Lst,
           double* __restrict__ y, double* __restrict__ uvec) {
     extern __shared__ double w[];
     __shared__ double xs[SB];
     __shared__ double part[4][SB];
-    const int s = batch[blockIdx.x];
-    const int f = S.sn_first[s];
-    const int ns = S.sn_first[s + 1] - f;
-    const int64_t rp = S.rows_ptr[s];
-    const int nr = (int)(S.rows_ptr[s + 1] - rp);
-    const int nf = ns + nr;
-    const int ld = S.ld[s];
+    const SolveDesc d = desc[blockIdx.x];        // one round trip instead of batch -> id -> six arrays
+    const int f = d.f, ns = d.ns, nr = d.nr, nf = ns + nr, ld = d.ld;
+    const int64_t rp = d.rows_ptr;
     const int tid = threadIdx.x;
     {
-        const int32_t* cp = S.asm_colptr + S.front_ptr[s];
-        const int64_t base = S.asm_base[s];
+        const int32_t* cp = S.asm_colptr + d.front_ptr;
+        const int64_t base = d.asm_base;
         for (int i = tid; i < nf; i += 256) {
             double acc = i < ns ? y[f + i] : 0.0;
             for (int e = cp[i]; e < cp[i + 1]; ++e) acc += uvec[S.asm_src[base + e]];
@@ -1393,7 +1502,7 @@ k_fwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
         }
     }
     __syncthreads();
-    const double* Lp = Lst + S.panel_off[s];
+    const double* Lp = Lst + d.panel_off;
     for (int kb = 0; kb < ns; kb += SB) {
         const int sb = min(SB, ns - kb);
         const double* blk = Lp + (int64_t)kb * ld;
@@ -1439,6 +1548,8 @@ k_bwd_cta(DevSym S, const int32_t* __restrict__ batch, const double* __restrict_
     extern __shared__ double w[];
     __shared__ double ts[SB];
     __shared__ double red8[8][8 * 33];
+    // (the packed descriptors of the warp kernels were measured here too: 13 % slower on C5 - the per-supernode
+    // index arrays are L2-resident, the 64-byte descriptors are not)
     const int s = batch[blockIdx.x];
     const int f = S.sn_first[s];
     const int ns = S.sn_first[s + 1] - f;

@@ -130,7 +130,12 @@ class B200DirectLDLSolver:
     def stream_ptr(self):
         return self._L.cb200_get_stream(self._h)
 
+    resident = False
+
     def set_resident(self, flag):
+        """Device-resident mode (include/clarabel_b200.h): pointer arguments of update_cones / setrhs are
+        then device pointers (B200KKTSolver.update_staged / setrhs_staged) or NULL (keep the state)."""
+        self.resident = bool(flag)
         self._L.cb200_set_resident(self._h, int(bool(flag)))
 
 
@@ -211,13 +216,32 @@ class B200KKTSolver:
             if not hasattr(self, "_ns_idx"):
                 self._ns_idx = nonsym_update_index(self.map, cones)
             self.ldl.update_values(self._ns_idx, nonsym_update_values(self.map, cones))
+        if self.ldl.resident:      # host arrays are not read in resident mode: refactor the state in HBM
+            return _lib.check(self.ldl._L.cb200_update_cones(self.ldl._h, *([None] * 6)), "cb200_update_cones")
         st = cones.export_state()
         arrs = [_c64(st[k]) for k in ("w", "soc_eta", "soc_d", "soc_u", "soc_v", "psd_R")]
         return _lib.check(self.ldl._L.cb200_update_cones(self.ldl._h, *[_p(a) for a in arrs]),
                           "cb200_update_cones")
 
+    STATE_KEYS = ("w", "soc_eta", "soc_d", "soc_u", "soc_v", "psd_R")
+
+    def update_staged(self, dev_ptrs):
+        """Resident mode: kktsolver_update! from a cone state the caller has staged in HBM.
+        dev_ptrs: device addresses (int, 0 = keep) in STATE_KEYS order."""
+        assert self.ldl.resident
+        args = [C.c_void_p(p) if p else None for p in dev_ptrs]
+        return _lib.check(self.ldl._L.cb200_update_cones(self.ldl._h, *args), "cb200_update_cones")
+
+    def setrhs_staged(self, px, pz):
+        """Resident mode: kktsolver_setrhs! from device addresses (stream-ordered device-to-device copy)."""
+        assert self.ldl.resident
+        _lib.check(self.ldl._L.cb200_setrhs(self.ldl._h, C.c_void_p(px) if px else None,
+                                            C.c_void_p(pz) if pz else None), "cb200_setrhs")
+
     def setrhs(self, rhsx, rhsz):
         # kktsolver_setrhs!: the right-hand side goes straight to the device (no host staging copy)
+        if self.ldl.resident:
+            return
         rx, rz = _c64(rhsx), _c64(rhsz)
         _lib.check(self.ldl._L.cb200_setrhs(self.ldl._h, _p(rx), _p(rz)), "cb200_setrhs")
 

@@ -178,9 +178,11 @@ int32_t cb200_dist_init(cb200_handle* h, int32_t rank, int32_t nranks, const cha
 /* The CUDA stream (cudaStream_t) all of this handle's work is enqueued on, so a caller can
  * bracket calls with its own events. */
 void*   cb200_get_stream(cb200_handle* h);
-/* resident != 0: cb200_update_cones / cb200_solve_ir skip their host<->device copies and work
- * on the cone state / right-hand side already in HBM from the previous call (device-resident
- * timing of the same kernels; results stay on the device). */
+/* resident != 0: the inputs live in HBM.  Non-NULL pointer arguments of cb200_update_cones and
+ * cb200_setrhs are then DEVICE pointers (copied device-to-device on the handle's stream), NULL
+ * keeps what the previous call left on the device; cb200_solve_ir ignores its host pointers and
+ * leaves the solution on the device (cb200_download selector 6).  This is the mode bench.py's
+ * device-resident `value` is measured in; the drop-in path (resident == 0) takes host pointers. */
 int32_t cb200_set_resident(cb200_handle* h, int32_t resident);
 const char* cb200_last_error(void);
 

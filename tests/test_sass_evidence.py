@@ -55,9 +55,13 @@ def test_pivot_kernels_use_dmma_or_registers_only(sass):
 
 
 @pytest.mark.parametrize("name,limit", [
-    ("k_piv_diag", 0), ("k_piv_rows", 0), ("k_fwd_warp", 0), ("k_bwd_warp", 12), ("k_fwd_cta", 0),
+    ("k_piv_diag", 0), ("k_piv_rows", 0), ("k_fwd_warp", 0), ("k_bwd_warp", 6), ("k_fwd_cta", 0),
     ("k_bwd_cta", 8), ("k_big_tri_fwd", 0), ("k_big_tri_bwd", 8), ("k_big_gemvT_bwd", 4),
     ("k_factor_panel", 8), ("k_factor_small", 0), ("k_ldl_update_tma", 0)])
 def test_no_collective_shuffles_in_hot_kernels(sass, name, limit):
-    n = sum(o == "WARPSYNC.COLLECTIVE" for o in _kernel(sass, name))
-    assert n <= limit, f"{name}: {n} WARPSYNC.COLLECTIVE"
+    """per instantiation: the limit is the number of __syncwarp() landing pads the kernel may have"""
+    hits = [k for k in sass if name in k]
+    assert hits, f"{name} not in the library"
+    for k in hits:
+        n = sum(o == "WARPSYNC.COLLECTIVE" for o in sass[k])
+        assert n <= limit, f"{k}: {n} WARPSYNC.COLLECTIVE"

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out/r02_determinism3.log; : > $O
+run() { env DET_SKIP_L=1 "$@" timeout 200 python tools/determinism.py C4r 300 2>&1 | grep -v "^$" | tail -12 >> $O; tail -1 $O | cut -c1-250; }
+run A=1; run CB200_TMA_TILE=128; run CB200_NO_TMA=1; run CB200_TMA_PAD_KB=100; run CB200_TMA_FENCE=1; run CB200_TMA_NATURAL=1; run CB200_MERGED_ROWS=0; run CB200_NO_PANEL=1

@@ -12,7 +12,8 @@ P, q, A, b, K = bench.make_problem(name)
 solver = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200"))
 ks = solver.kktsystem.kktsolver
 rec = bench.Recorder(ks)
-sol = solver.solve()
+_mi = int(os.environ.get("CB200_MAX_ITER", "0"))
+sol = solver.solve(max_iter=_mi) if _mi else solver.solve()
 rec.detach()
 for row in solver.iter_log[-5:]:
     print("   it %d pcost %.10e dcost %.10e pres %.2e dres %.2e mu %.2e step %.3f" % row)
