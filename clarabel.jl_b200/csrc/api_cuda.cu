@@ -1109,7 +1109,11 @@ int32_t cb200_create(int64_t N, const int64_t* colptr, const int64_t* rowval, co
         CUDA_OK(cudaFuncSetAttribute(k_piv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * PB * (PB + 1)) * (int)sizeof(double)));
         CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_gemm_smem(128)));
-        CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        {   // (CB200_TMA_ATTR_KB: debugging aid, see DESIGN.md section 8 "reproducibility")
+            const char* e = getenv("CB200_TMA_ATTR_KB");
+            const int attr = e ? atoi(e) * 1024 + 64 : 200 * 1024;
+            CUDA_OK(cudaFuncSetAttribute(k_ldl_update_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr));
+        }
         { int rct = build_tensor_maps(h); if (rct) return rct; }
         CUDA_OK(cudaFuncSetAttribute(k_fwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_OK(cudaFuncSetAttribute(k_bwd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

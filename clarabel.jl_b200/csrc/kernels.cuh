@@ -718,6 +718,17 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
 #pragma unroll
         for (int v = 0; v < 4; ++v) { const int k = u.k0 + it * TK + 4 * v + t; dv[v] = (k < u.k1) ? Dv[k] : 0.0; }
         mbar_wait(full + st, ph);
+        // Release of the PREVIOUS stage, one iteration late and after the wait above.  Releasing a stage at
+        // the end of its own iteration is not safe: ptxas schedules the SYNCS.ARRIVE right behind the last
+        // LDS *issue* (before the DMMAs that consume them - it did, see profiles/r02_tma_release_race.md),
+        // the arrive does not wait for loads in flight, and with 3 CTAs per SM an LDS can be overtaken by
+        // the TMA refill of its stage: ~1 corrupted tile per 1e6, 3-5 % of the C4r factorisations.  Here
+        // every DMMA of stage it-1 was issued before the spin-wait (they cannot sink below its loop), a DMMA
+        // issues only when its LDS operands have arrived, and the arrive cannot rise above the acquire.
+        if (it > 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + (it - 1) % TSTAGES);
+        }
         const double* A = sA + st * TTILE + (wm / 8) * srg + g;
         const double* B = sB + st * TTILE + (wn / 8) * srg + g;
         double bf[NJ][4];
@@ -735,9 +746,6 @@ k_ldl_update_tma(DevSym S, const int32_t* __restrict__ batch, const CUtensorMap*
 #pragma unroll
             for (int j = 0; j < NJ; ++j) dmma16816(acc[i][j], af, bf[j]);
         }
-        if (kmajor & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // debugging aid (CB200_TMA_FENCE)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
     }
     // ===== epilogue: subtract into the panel (col < ns) or the update block.  All loads of a column
     // pair are issued before the first store (a plain  *p -= v  loop serialises 64 load->store chains).

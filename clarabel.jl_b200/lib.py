@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclarabel_b200.so")
+LIB_PATH = os.environ.get("CB200_LIB_PATH") or os.path.join(_HERE, "libclarabel_b200.so")    # (override: dev builds)
 _LIB = None
 
 # every symbol include/clarabel_b200.h declares

@@ -172,3 +172,35 @@ def test_c4_full_size_sdp(cb):
     assert ks.update(__import__("bench").FakeCones(last["state"]))
     got = ks.device_nzval()[ks.map.Hsblocks[cones.rng_blocks[i0]:cones.rng_blocks[i0 + 1]]]
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_refactorisation_is_bitwise_reproducible(cb):
+    """Same inputs -> same bits.  Guards the dense-front GEMM pipeline (a stage released before its
+    shared-memory reads had completed corrupted ~4 % of the factorisations of this instance, never the same
+    tile twice): the reduced SDP is refactored 40 times with the large panel download in between (the
+    protocol that exposed it) and pivots and solutions must be identical every time."""
+    import bench
+    P, q, A, b, K = bench.make_problem("C4r")
+    solver = cb.Solver(P, q, A, b, K, cb.Settings(direct_solve_method="b200"))
+    ks = solver.kktsystem.kktsolver
+    rec = bench.Recorder(ks)
+    solver.solve(max_iter=6)
+    rec.detach()
+    st = [s for s in rec.steps if len(s["rhs"]) == 3][-1]
+    N, n, m = ks.KKT.shape[0], ks.n, ks.m
+    npanel = int(ks.ldl.stats()["panel_bytes"] // 8)
+    rx, rz = st["rhs"][0]
+    ref = None
+    for r in range(40):
+        assert ks.update(bench.FakeCones(st["state"]))
+        D = ks.ldl.download(1, N)
+        L = ks.ldl.download(2, npanel)
+        gx, gz = np.zeros(n), np.zeros(m)
+        ks.setrhs(rx, rz); assert ks.solve(gx, gz)
+        x = ks.ldl.download(6, N)
+        if ref is None:
+            ref = (D, L, x)
+            continue
+        assert np.array_equal(D, ref[0]), f"repeat {r}: pivots differ"
+        assert np.array_equal(L, ref[1]), f"repeat {r}: panels differ"
+        assert np.array_equal(x, ref[2]), f"repeat {r}: solutions differ"

@@ -65,3 +65,24 @@ def test_no_collective_shuffles_in_hot_kernels(sass, name, limit):
     for k in hits:
         n = sum(o == "WARPSYNC.COLLECTIVE" for o in sass[k])
         assert n <= limit, f"{k}: {n} WARPSYNC.COLLECTIVE"
+
+
+def test_tma_gemm_releases_a_stage_only_after_the_next_wait(sass):
+    """The consumer warps' mbarrier arrive on the `empty` barrier (SYNCS.ARRIVE...A1T0, lane 0 only) must sit
+    directly behind the try-wait of the NEXT stage, before any shared-memory load or DMMA of that stage: every
+    DMMA of the released stage has then been issued (they cannot sink below the spin loop), i.e. every LDS of it
+    has completed.  With the arrive at the end of the stage's own iteration ptxas put it behind the last LDS
+    issue and ahead of the DMMAs, and ~1 tile in 1e6 was computed from a refilled stage
+    (profiles/r02_tma_release_race.md)."""
+    hits = [k for k in sass if "k_ldl_update_tma" in k]
+    assert len(hits) >= 2
+    for k in hits:
+        ops = sass[k]
+        idx = [i for i, o in enumerate(ops) if o.startswith("SYNCS.ARRIVE") and o.endswith("A1T0")]
+        assert idx, f"{k}: consumer arrive not found"
+        for i in idx:
+            j = i - 1
+            while j >= 0 and "TRYWAIT" not in ops[j]:
+                assert not ops[j].startswith(("LDS", "DMMA")), f"{k}: {ops[j]} between the wait and the release"
+                j -= 1
+            assert j >= 0
