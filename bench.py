@@ -461,6 +461,25 @@ def main():
         gsol.append(np.concatenate([gx, gz]))
         gfull.append(ks.ldl.download(6, N))     # [x; z; expansion variables] as the device holds it
     par_ir = ks.ir_rounds / max(1, ks.n_solves)
+    # the device-resident leg must compute the same thing: the same system once more from the staged
+    # (HBM) copies of its inputs, solutions compared with the host-buffer path above
+    res_diff = None
+    try:
+        ks.ldl.set_resident(True)
+        st_t, rhs_t = staged[-1]
+        okr = ks.update_staged([st_t[key].data_ptr() if st_t[key].numel() else 0 for key in ks.STATE_KEYS])
+        res_diff = 0.0
+        for (tx, tz), xh in zip(rhs_t, gfull):
+            ks.setrhs_staged(tx.data_ptr() if tx.numel() else 0, tz.data_ptr() if tz.numel() else 0)
+            okr &= ks.solve(None, None)
+            xr = ks.ldl.download(6, N)
+            res_diff = max(res_diff, float(np.abs(xr - xh).max() / max(1e-300, np.abs(xh).max())))
+        if not okr:
+            res_diff = float("inf")
+    except Exception as e:        # never lose the line over the cross-check
+        res_diff = f"failed: {e}"
+    finally:
+        ks.ldl.set_resident(False)
     nreg = int(ks.ldl.download(5, 1)[0])
     if world > 1:
         import torch.distributed as dist
@@ -482,7 +501,7 @@ def main():
                   regularised_pivots=nreg, gpu_solve=dict(status=sol.status_name, iterations=int(sol.iterations),
                                                           obj_val=float(sol.obj_val), obj_val_dual=float(sol.obj_val_dual),
                                                           r_prim=float(sol.r_prim), r_dual=float(sol.r_dual)),
-                  cpu_rel_diff=None)
+                  resident_vs_host_rel_diff=res_diff, cpu_rel_diff=None)
     info = ks.ldl.info()
     stats = ks.ldl.stats()
     peaks = {}

@@ -96,6 +96,44 @@ def test_cone_update_and_regularisation_match_oracle(cb, b200, name):
     gpu.setrhs(rx, rz); assert gpu.solve(None, zg)
 
 
+@pytest.mark.parametrize("name", ["C3s", "C4s"])
+def test_resident_mode_takes_device_pointers(cb, b200, name):
+    """cb200_set_resident: update_cones / setrhs then take DEVICE pointers (inputs staged in HBM, the mode
+    bench.py's device-resident `value` is measured in).  Same bits as the host-buffer path."""
+    import torch
+    s = _iterate_cones(cb, small_instances(cb)[name])
+    data, cones, st = s.data, s.cones, s.settings
+    gpu = b200.B200KKTSolver(data.P, data.A, cones, data.m, data.n, st)
+    N = gpu.KKT.shape[0]
+    rng = np.random.default_rng(11)
+    rx, rz = rng.standard_normal(data.n), rng.standard_normal(data.m)
+    assert gpu.update(cones)
+    xg, zg = np.zeros(data.n), np.zeros(data.m)
+    gpu.setrhs(rx, rz); assert gpu.solve(xg, zg)
+    x_host = gpu.ldl.download(6, N)
+    D_host = gpu.ldl.download(1, N)
+    state = cones.export_state()
+    dev = {k: torch.from_numpy(np.ascontiguousarray(state[k], dtype=np.float64)).cuda() for k in gpu.STATE_KEYS}
+    tx, tz = torch.from_numpy(rx).cuda(), torch.from_numpy(rz).cuda()
+    torch.cuda.synchronize()
+    gpu.ldl.set_resident(True)
+    try:
+        assert gpu.update_staged([dev[k].data_ptr() if dev[k].numel() else 0 for k in gpu.STATE_KEYS])
+        gpu.setrhs_staged(tx.data_ptr(), tz.data_ptr())
+        assert gpu.solve(None, None)
+        assert np.array_equal(gpu.ldl.download(1, N), D_host)
+        assert np.array_equal(gpu.ldl.download(6, N), x_host)
+        # NULL pointers keep the state in HBM: same factorisation again
+        assert gpu.update_staged([0] * len(gpu.STATE_KEYS))
+        assert np.array_equal(gpu.ldl.download(1, N), D_host)
+    finally:
+        gpu.ldl.set_resident(False)
+    # back on the host-buffer path
+    x2, z2 = np.zeros(data.n), np.zeros(data.m)
+    gpu.setrhs(rx, rz); assert gpu.solve(x2, z2)
+    assert np.array_equal(x2, xg) and np.array_equal(z2, zg)
+
+
 def _rel(a, b):
     return abs(a - b) / max(1.0, abs(b))
 
