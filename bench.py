@@ -72,8 +72,11 @@ def make_problem(name):
 def workload_config(name, data, N, nnzK):
     """Identical in both arms: what the instance is, nothing about how an arm solves it."""
     gen, kw = WORKLOADS[name]
+    # factor storage per step: C3 0.4 GB, C4 4.2 GB, C5 1.6 GB (>> the 126 MB L2); C1 2 MB, C2 58 MB
+    l2 = ("working set fits in the 126 MB L2 and is NOT flushed between steps (latency-bound parity config)"
+          if name in ("C1", "C2", "C4t") else "inputs larger than L2 (no flush)")
     return dict(workload=name, generator=gen, generator_kwargs=kw, n=int(data.n), m=int(data.m),
-                N=int(N), nnzK=int(nnzK), l2="inputs larger than L2 (no flush)")
+                N=int(N), nnzK=int(nnzK), l2=l2)
 
 
 class Recorder:
